@@ -1,0 +1,380 @@
+"""ctypes binding of `libbsi.so` (C ABI in `include/bsi.h`).
+
+The library is the product: there is no Python or CPU implementation of the path behind it, and a
+missing library or missing CUDA device is an error, never a fallback.
+"""
+import ctypes as C
+import os
+from math import inf
+
+import numpy as np
+
+from .constants import range_name
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libbsi.so')
+
+BSI_INF = 2 ** 64 - 1
+KEY_WORDS_MAX = 4
+MODE_SIMULATE, MODE_ATTRACT, MODE_TARGET = 0, 1, 2
+_RANGE_CODE = {'TRUE_OR_FALSE': 0, 'MAYBE_FALSE': 1, 'MAYBE_TRUE': 2, 'MAYBE_TRUE_OR_FALSE': 3}
+STATUS_NAMES = {0: 'BSI_OK', -1: 'BSI_E_ARG', -2: 'BSI_E_CUDA', -3: 'BSI_E_NVRTC',
+                -4: 'BSI_E_CAPACITY', -5: 'BSI_E_UNSUPPORTED', -6: 'BSI_E_NOMEM'}
+
+#: every symbol include/bsi.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    'bsi_abi_version', 'bsi_last_error', 'bsi_device_count', 'bsi_plan_create',
+    'bsi_plan_create_offline', 'bsi_plan_destroy', 'bsi_plan_n_problems', 'bsi_plan_key_words',
+    'bsi_plan_set_stream', 'bsi_plan_source', 'bsi_plan_build_log', 'bsi_plan_cubin',
+    'bsi_plan_launch_config', 'bsi_plan_op_counts', 'bsi_compile_only', 'bsi_attract_run',
+    'bsi_attract_table_clear', 'bsi_attract_table_count', 'bsi_attract_table_read',
+    'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
+    'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
+]
+
+
+class BsiError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__('%s: %s' % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class NetworkDesc(C.Structure):
+    _fields_ = [('n_nodes', C.c_uint32), ('pred_off', C.c_void_p), ('pred_idx', C.c_void_p),
+                ('tt_off', C.c_void_p), ('tt', C.c_void_p)]
+
+
+class SpaceDesc(C.Structure):
+    _fields_ = [('initial_state', C.c_void_p),
+                ('n_fixed', C.c_uint32), ('fixed_node', C.c_void_p), ('fixed_value', C.c_void_p),
+                ('n_perturbations', C.c_uint32), ('pert_t', C.c_void_p), ('pert_node', C.c_void_p),
+                ('pert_value', C.c_void_p),
+                ('n_variations', C.c_uint32), ('var_kind', C.c_void_p), ('var_node', C.c_void_p),
+                ('var_t', C.c_void_p), ('var_range', C.c_void_p)]
+
+
+class TargetDesc(C.Structure):
+    _fields_ = [('mask', C.c_uint64 * KEY_WORDS_MAX), ('code', C.c_uint64 * KEY_WORDS_MAX)]
+
+
+class PlanOpts(C.Structure):
+    _fields_ = [('first_horizon', C.c_uint32), ('filter_nodes', C.c_uint32),
+                ('table_log2_slots', C.c_uint32), ('chunk_log2', C.c_uint32),
+                ('keep_source', C.c_uint32), ('block_threads', C.c_uint32),
+                ('min_blocks', C.c_uint32), ('reserved', C.c_uint32 * 9)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [('n_problems', C.c_uint64), ('n_found', C.c_uint64), ('n_without', C.c_uint64),
+                ('steps', C.c_uint64), ('device_steps', C.c_uint64), ('launches', C.c_uint64),
+                ('rounds', C.c_uint64), ('ms_total', C.c_double), ('ms_main', C.c_double),
+                ('ms_resolve', C.c_double), ('reserved', C.c_uint64 * 6)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != 'reserved'}
+
+
+ATTRACTOR_REC = np.dtype([('key', np.uint64, (KEY_WORDS_MAX,)), ('n', np.uint64),
+                          ('sum_l', np.uint64), ('sum_l2', np.uint64), ('lam', np.uint64)])
+
+_lib = None
+
+
+def lib():
+    """Load libbsi.so; raises if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsiError(-2, 'libbsi.so is not built (%s); run __graft_entry__.build(). There is '
+                               'no CPU fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        p, u64, u32, i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+        L.bsi_abi_version.restype = i
+        L.bsi_last_error.restype = C.c_char_p
+        L.bsi_device_count.argtypes = [C.POINTER(i)]
+        L.bsi_plan_create.argtypes = [C.POINTER(NetworkDesc), C.POINTER(SpaceDesc), i,
+                                      C.POINTER(TargetDesc), C.POINTER(PlanOpts), i, C.POINTER(p)]
+        L.bsi_plan_create_offline.argtypes = [C.POINTER(NetworkDesc), C.POINTER(SpaceDesc), i,
+                                              C.POINTER(TargetDesc), C.POINTER(PlanOpts),
+                                              C.POINTER(p)]
+        L.bsi_plan_destroy.argtypes = [p]
+        L.bsi_plan_destroy.restype = None
+        L.bsi_plan_n_problems.argtypes = [p, C.POINTER(u64)]
+        L.bsi_plan_key_words.argtypes = [p, C.POINTER(u32)]
+        L.bsi_plan_set_stream.argtypes = [p, p]
+        L.bsi_plan_source.argtypes = [p]
+        L.bsi_plan_source.restype = C.c_char_p
+        L.bsi_plan_build_log.argtypes = [p]
+        L.bsi_plan_build_log.restype = C.c_char_p
+        L.bsi_plan_cubin.argtypes = [p, C.POINTER(p), C.POINTER(u64)]
+        L.bsi_plan_launch_config.argtypes = [p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.bsi_plan_op_counts.argtypes = [p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.bsi_compile_only.argtypes = [C.POINTER(NetworkDesc), C.POINTER(SpaceDesc), i,
+                                       C.POINTER(TargetDesc), C.POINTER(PlanOpts),
+                                       C.POINTER(u64), C.c_char_p, u64]
+        L.bsi_attract_run.argtypes = [p, u64, u64, u64, u64, C.POINTER(RunStats)]
+        L.bsi_attract_table_clear.argtypes = [p]
+        L.bsi_attract_table_count.argtypes = [p, C.POINTER(u64)]
+        L.bsi_attract_table_read.argtypes = [p, p, u64, C.POINTER(u64)]
+        L.bsi_attract_table_export_device.argtypes = [p, p, u64, C.POINTER(u64)]
+        L.bsi_attract_table_merge_device.argtypes = [p, p, u64]
+        L.bsi_attractor_states.argtypes = [p, p, u64, p]
+        L.bsi_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
+        L.bsi_simulate_list.argtypes = [p, p, u64, u64, p, C.POINTER(RunStats)]
+        L.bsi_target_run.argtypes = [p, u64, u64, u64, p, p, u64, C.POINTER(u64),
+                                     C.POINTER(RunStats)]
+        L.bsi_measure_lop3_peak.argtypes = [i, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(i)]
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise BsiError(status, lib().bsi_last_error().decode('utf-8', 'replace'))
+
+
+def cap(value):
+    """`math.inf` / None (reference cli.py:241-242) -> BSI_INF."""
+    return BSI_INF if value is None or value == inf else int(value)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def words_from_code(code, kw):
+    return np.array([(code >> (64 * j)) & (2 ** 64 - 1) for j in range(kw)], np.uint64)
+
+
+def code_from_words(words):
+    v = 0
+    for j, w in enumerate(words):
+        v |= int(w) << (64 * j)
+    return v
+
+
+class PackedProblem:
+    """The reference's Python structures packed into the C descriptors.
+
+    Arguments are exactly what `parse_input` produces and the `*_master` functions take
+    (reference input.py:124-157): predecessor lists, truth-table dicts, the origin simulation
+    problem `(initial_state, fixed_nodes, perturbed_nodes_by_t)` and its variations
+    `(initial nodes, [(node, range)], [(t, node, range)])`.  Keeps the numpy arrays alive.
+    """
+
+    def __init__(self, predecessor_node_lists, truth_tables, origin_simulation_problem,
+                 simulation_problem_variations):
+        n = len(predecessor_node_lists)
+        self.n_nodes = n
+        self.kw = max(1, (n + 63) // 64)
+        pred_off = np.zeros(n + 1, np.uint32)
+        tt_off = np.zeros(n + 1, np.uint64)
+        pred_idx, tt = [], []
+        for i, (preds, table) in enumerate(zip(predecessor_node_lists, truth_tables)):
+            k = len(preds)
+            pred_idx.extend(int(q) for q in preds)
+            for j in range(1 << k):
+                # first predecessor = most significant bit of j (input.py:881, model.py:26-27)
+                key = tuple(bool((j >> (k - 1 - m)) & 1) for m in range(k))
+                tt.append(1 if table[key] else 0)
+            pred_off[i + 1] = len(pred_idx)
+            tt_off[i + 1] = len(tt)
+        initial_state, fixed_nodes, perturbed_nodes_by_t = origin_simulation_problem
+        var_initial, var_fixed, var_perturbed = simulation_problem_variations
+        a = self.arrays = {
+            'pred_off': pred_off, 'pred_idx': np.array(pred_idx + [0], np.uint32),
+            'tt_off': tt_off, 'tt': np.array(tt + [0], np.uint8),
+            'initial_state': np.array([1 if v else 0 for v in initial_state], np.uint8),
+            'fixed_node': np.array(list(fixed_nodes.keys()) + [0], np.uint32),
+            'fixed_value': np.array([1 if v else 0 for v in fixed_nodes.values()] + [0], np.uint8),
+        }
+        pt, pn, pv = [], [], []
+        for t, nodes in perturbed_nodes_by_t.items():
+            for node, value in nodes.items():
+                pt.append(int(t)), pn.append(int(node)), pv.append(1 if value else 0)
+        a['pert_t'] = np.array(pt + [0], np.uint64)
+        a['pert_node'] = np.array(pn + [0], np.uint32)
+        a['pert_value'] = np.array(pv + [0], np.uint8)
+        vk, vn, vt, vr = [], [], [], []
+        for node in var_initial:
+            vk.append(0), vn.append(int(node)), vt.append(0), vr.append(0)
+        for node, r in var_fixed:
+            vk.append(1), vn.append(int(node)), vt.append(0), vr.append(_RANGE_CODE[range_name(r)])
+        for t, node, r in var_perturbed:
+            vk.append(2), vn.append(int(node)), vt.append(int(t)), vr.append(_RANGE_CODE[range_name(r)])
+        a['var_kind'] = np.array(vk + [0], np.uint32)
+        a['var_node'] = np.array(vn + [0], np.uint32)
+        a['var_t'] = np.array(vt + [0], np.uint64)
+        a['var_range'] = np.array(vr + [0], np.uint32)
+        self.n_problems = 1
+        for r in vr:
+            self.n_problems *= 3 if r == 3 else 2
+        net = self.network = NetworkDesc()
+        net.n_nodes = n
+        for name in ('pred_off', 'pred_idx', 'tt_off', 'tt'):
+            setattr(net, name, _ptr(a[name]))
+        sp = self.space = SpaceDesc()
+        sp.n_fixed, sp.n_perturbations, sp.n_variations = len(fixed_nodes), len(pt), len(vk)
+        for name in ('initial_state', 'fixed_node', 'fixed_value', 'pert_t', 'pert_node',
+                     'pert_value', 'var_kind', 'var_node', 'var_t', 'var_range'):
+            setattr(sp, name, _ptr(a[name]))
+
+
+def make_target(target_node_set, target_substate_code, kw):
+    t = TargetDesc()
+    mask = sum(1 << int(i) for i in target_node_set)
+    for j in range(KEY_WORDS_MAX):
+        t.mask[j] = (mask >> (64 * j)) & (2 ** 64 - 1)
+        t.code[j] = (int(target_substate_code) >> (64 * j)) & (2 ** 64 - 1)
+    return t
+
+
+class Plan:
+    """Owner of one `bsi_plan*` (network + problem space + mode specialised for one device)."""
+
+    def __init__(self, packed, mode, device=0, target=None, offline=False, **opts):
+        self.packed = packed
+        self.mode = mode
+        self.kw = packed.kw
+        self._h = C.c_void_p()
+        o = PlanOpts()
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError('unknown plan option %r' % k)
+            setattr(o, k, int(v))
+        tptr = C.byref(target) if target is not None else None
+        if offline:
+            check(lib().bsi_plan_create_offline(C.byref(packed.network), C.byref(packed.space),
+                                                mode, tptr, C.byref(o), C.byref(self._h)))
+        else:
+            check(lib().bsi_plan_create(C.byref(packed.network), C.byref(packed.space), mode, tptr,
+                                        C.byref(o), int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().bsi_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- introspection -------------------------------------------------------------------
+    @property
+    def n_problems(self):
+        n = C.c_uint64()
+        check(lib().bsi_plan_n_problems(self._h, C.byref(n)))
+        return n.value
+
+    def source(self):
+        return lib().bsi_plan_source(self._h).decode()
+
+    def build_log(self):
+        return lib().bsi_plan_build_log(self._h).decode()
+
+    def cubin(self):
+        data, size = C.c_void_p(), C.c_uint64()
+        check(lib().bsi_plan_cubin(self._h, C.byref(data), C.byref(size)))
+        return C.string_at(data, size.value)
+
+    def op_counts(self):
+        u, c, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().bsi_plan_op_counts(self._h, C.byref(u), C.byref(c), C.byref(f)))
+        return {'update_lop3': u.value, 'compare_lop3': c.value, 'filter_lop3': f.value}
+
+    def launch_config(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().bsi_plan_launch_config(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {'n_sms': a.value, 'block_threads': b.value, 'blocks_per_sm': c.value}
+
+    def set_stream(self, cuda_stream):
+        check(lib().bsi_plan_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # ---- attract -------------------------------------------------------------------------
+    def attract_run(self, idx_begin, idx_end, max_t=inf, max_attractor_l=inf):
+        st = RunStats()
+        check(lib().bsi_attract_run(self._h, int(idx_begin), int(idx_end), cap(max_t),
+                                    cap(max_attractor_l), C.byref(st)))
+        return st.as_dict()
+
+    def table_clear(self):
+        check(lib().bsi_attract_table_clear(self._h))
+
+    def table_count(self):
+        n = C.c_uint64()
+        check(lib().bsi_attract_table_count(self._h, C.byref(n)))
+        return n.value
+
+    def table_read(self):
+        """-> structured array of ATTRACTOR_REC (unsorted)."""
+        n = self.table_count()
+        out = np.zeros(max(n, 1), ATTRACTOR_REC)
+        got = C.c_uint64()
+        check(lib().bsi_attract_table_read(self._h, _ptr(out), max(n, 1), C.byref(got)))
+        return out[:got.value]
+
+    def table_export_device(self, dev_ptr, capacity):
+        n = C.c_uint64()
+        check(lib().bsi_attract_table_export_device(self._h, C.c_void_p(dev_ptr), int(capacity),
+                                                    C.byref(n)))
+        return n.value
+
+    def table_merge_device(self, dev_ptr, n):
+        check(lib().bsi_attract_table_merge_device(self._h, C.c_void_p(dev_ptr), int(n)))
+
+    def attractor_states(self, key, lam):
+        """Orbit of the key state: `lam` state codes, key first (attract.py:22-25)."""
+        kwords = words_from_code(int(key), self.kw)
+        out = np.zeros((int(lam), self.kw), np.uint64)
+        check(lib().bsi_attractor_states(self._h, _ptr(kwords), int(lam), _ptr(out)))
+        return [code_from_words(row) for row in out]
+
+    # ---- simulate / target -----------------------------------------------------------------
+    def simulate_run(self, idx_begin, idx_end, max_t):
+        n = int(idx_end) - int(idx_begin)
+        out = np.zeros((max(n, 1), int(max_t) + 1, self.kw), np.uint64)
+        st = RunStats()
+        check(lib().bsi_simulate_run(self._h, int(idx_begin), int(idx_end), int(max_t), _ptr(out),
+                                     C.byref(st)))
+        return out[:n], st.as_dict()
+
+    def simulate_list(self, indices, max_t):
+        idx = np.ascontiguousarray(indices, np.uint64)
+        out = np.zeros((max(len(idx), 1), int(max_t) + 1, self.kw), np.uint64)
+        st = RunStats()
+        check(lib().bsi_simulate_list(self._h, _ptr(idx), len(idx), int(max_t), _ptr(out),
+                                      C.byref(st)))
+        return out[:len(idx)], st.as_dict()
+
+    def target_run(self, idx_begin, idx_end, max_t=inf, n_to_find=inf):
+        n = int(idx_end) - int(idx_begin)
+        capacity = n if n_to_find is None or n_to_find == inf else min(n, int(n_to_find))
+        hit_index = np.zeros(max(capacity, 1), np.uint64)
+        hit_t = np.zeros(max(capacity, 1), np.uint64)
+        got = C.c_uint64()
+        st = RunStats()
+        check(lib().bsi_target_run(self._h, int(idx_begin), int(idx_end), cap(max_t),
+                                   _ptr(hit_index), _ptr(hit_t), capacity, C.byref(got),
+                                   C.byref(st)))
+        return hit_index[:got.value], hit_t[:got.value], st.as_dict()
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().bsi_device_count(C.byref(n)))
+    return n.value
+
+
+def measure_lop3_peak(device=0):
+    ops, mhz, sms = C.c_double(), C.c_double(), C.c_int()
+    check(lib().bsi_measure_lop3_peak(int(device), C.byref(ops), C.byref(mhz), C.byref(sms)))
+    return {'lop3_per_s': ops.value, 'implied_sm_mhz': mhz.value, 'n_sms': sms.value}

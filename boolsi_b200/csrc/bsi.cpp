@@ -1,0 +1,973 @@
+// libbsi -- host side of the C ABI declared in include/bsi.h.
+//
+// A plan = one network + problem space + mode, specialised through NVRTC into the hand-written
+// kernel template (bsi_template.cuh) for sm_100a, loaded with the CUDA driver API (libcuda is
+// opened lazily with dlopen so that the library itself loads -- and can specialise kernels --
+// on a machine without a GPU; every run entry point fails with BSI_E_CUDA there: there is no
+// CPU fallback).
+//
+// What the run functions replace in the reference: the batch/problem loops of
+// mpi.py:131-190, 498-544 and the per-mode solvers of attract.py:262-455, target.py:109-133,
+// simulate.py:97-178 (see include/bsi.h for the per-function citations).
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "bsi_codegen.hpp"
+#include "bsi_template_inc.h"   // generated from bsi_template.cuh: bsi_template_src[]
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+// ---- CUDA driver API, bound at first use -------------------------------------------------------
+#define BSI_STR2(x) #x
+#define BSI_STR(x) BSI_STR2(x)
+#define BSI_CU_FUNCS(X)                                                                          \
+    X(cuInit) X(cuDeviceGetCount) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDeviceGetName)       \
+    X(cuDevicePrimaryCtxRetain) X(cuDevicePrimaryCtxRelease) X(cuCtxPushCurrent)                  \
+    X(cuCtxPopCurrent) X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction)               \
+    X(cuFuncSetAttribute) X(cuFuncGetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor)    \
+    X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemsetD8Async) X(cuMemcpyDtoHAsync)          \
+    X(cuMemcpyHtoDAsync) X(cuMemcpyDtoDAsync) X(cuStreamSynchronize) X(cuStreamCreate)            \
+    X(cuStreamDestroy) X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize)                    \
+    X(cuEventElapsedTime) X(cuEventDestroy) X(cuGetErrorString) X(cuMemAllocHost)                 \
+    X(cuMemFreeHost)
+
+struct CuApi {
+#define X(name) decltype(&name) p_##name = nullptr;
+    BSI_CU_FUNCS(X)
+#undef X
+    bool ok = false;
+    std::string why;
+};
+
+CuApi &cu() {
+    static CuApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { api.why = "libcuda.so.1 not found (no NVIDIA driver): libbsi has no CPU fallback"; return; }
+        // cuda.h maps the plain names to their current versioned symbols (e.g. cuMemAlloc_v2)
+#define X(name)                                                                                   \
+        api.p_##name = (decltype(&name))dlsym(h, BSI_STR(name));                                  \
+        if (!api.p_##name) { api.why = std::string("missing driver symbol ") + BSI_STR(name); return; }
+        BSI_CU_FUNCS(X)
+#undef X
+        CUresult r = api.p_cuInit(0);
+        if (r != CUDA_SUCCESS) { api.why = "cuInit failed (" + std::to_string((int)r) + ")"; return; }
+        api.ok = true;
+    });
+    return api;
+}
+
+const char *cu_errstr(CUresult r) {
+    const char *s = nullptr;
+    if (cu().p_cuGetErrorString && cu().p_cuGetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+    return "unknown CUDA error";
+}
+
+#define CU_CHECK(call)                                                                            \
+    do {                                                                                          \
+        CUresult r_ = cu().p_##call;                                                              \
+        if (r_ != CUDA_SUCCESS)                                                                   \
+            return fail(BSI_E_CUDA, "%s failed: %s (%s:%d)", #call, cu_errstr(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// mirrors of the device structs in bsi_template.cuh
+struct Counters {
+    uint64_t next_word, next_word2, next_word3, n_found, n_retry;
+    uint64_t n_without, n_accepted, steps, device_steps, table_full, n_hits, internal_error;
+    uint64_t pad[4];
+};
+constexpr size_t kPerRoundBytes = 5 * sizeof(uint64_t);
+constexpr int kMaxCk = 72;
+struct Sched {
+    uint32_t n_ck, end;
+    uint32_t ck_time[kMaxCk];
+    uint32_t ck_slot[kMaxCk];
+};
+
+// Checkpoint schedule for horizon H >= 1 (see the header comment of bsi_template.cuh).
+Sched make_sched(uint64_t H) {
+    Sched s{};
+    const uint64_t c1 = (H + 2) / 3, c2 = (2 * H + 2) / 3, c3 = H;
+    auto push = [&](uint64_t t, uint32_t slot) {
+        s.ck_time[s.n_ck] = (uint32_t)t;
+        s.ck_slot[s.n_ck] = slot;
+        ++s.n_ck;
+    };
+    // early detection: 0, 1, 2, 3, 4, 6, 8, 12, 16, 24, ... while below the first final checkpoint
+    if (c1 > 0) push(0, 0);
+    for (uint64_t p = 1; p < c1; p *= 2) {
+        push(p, 0);
+        if (p >= 2 && p + p / 2 < c1) push(p + p / 2, 0);
+    }
+    uint64_t finals[3] = {c1, c2, c3};
+    uint64_t prev = 0, max_gap = 0;
+    uint32_t slot = 0;
+    bool first = true;
+    for (uint64_t c : finals) {
+        if (!first && c == prev) continue;
+        // a lane with prev < mu <= c (first: 0 <= mu <= c) has lambda <= H - mu
+        uint64_t gap = first ? c : c - prev - 1;
+        max_gap = std::max(max_gap, gap);
+        push(c, slot++);
+        prev = c;
+        first = false;
+    }
+    s.end = (uint32_t)(H + max_gap);
+    return s;
+}
+
+struct DevBuf {
+    CUdeviceptr p = 0;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct bsi_plan {
+    bsi::Model m;
+    bsi::GenInfo info;
+    bsi_plan_opts opts{};
+    std::string source, log;
+    std::vector<char> cubin;
+    int block = 64;
+    int device = -1;           // -1: compile-only plan
+    CUdevice dev = 0;
+    CUcontext ctx = nullptr;
+    CUmodule mod = nullptr;
+    CUstream own_stream = nullptr, stream = nullptr;
+    CUfunction f_dense = nullptr, f_queue = nullptr, f_key = nullptr, f_mu = nullptr,
+               f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
+    int n_sms = 0;
+    int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
+    size_t main_smem = 0;
+    uint32_t table_log2 = 20;
+    DevBuf ctr, table, found_q, retry_q[2], scratch, misc, misc2, misc3;
+    std::vector<CUevent> events;
+    size_t events_used = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct CtxGuard {
+    bool pushed = false;
+    explicit CtxGuard(bsi_plan *p) {
+        if (p && p->ctx && cu().ok) pushed = cu().p_cuCtxPushCurrent(p->ctx) == CUDA_SUCCESS;
+    }
+    ~CtxGuard() {
+        if (pushed) { CUcontext c; cu().p_cuCtxPopCurrent(&c); }
+    }
+};
+
+int ensure(bsi_plan *p, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return BSI_OK;
+    if (b.p) { cu().p_cuMemFree(b.p); b.p = 0; b.bytes = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    CUresult r = cu().p_cuMemAlloc(&b.p, want);
+    if (r != CUDA_SUCCESS) {
+        b.p = 0;
+        return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? BSI_E_NOMEM : BSI_E_CUDA,
+                    "cuMemAlloc(%zu bytes) failed: %s", want, cu_errstr(r));
+    }
+    b.bytes = want;
+    (void)p;
+    return BSI_OK;
+}
+
+int get_event(bsi_plan *p, CUevent *out) {
+    if (p->events_used == p->events.size()) {
+        CUevent e;
+        CU_CHECK(cuEventCreate(&e, CU_EVENT_DEFAULT));
+        p->events.push_back(e);
+    }
+    *out = p->events[p->events_used++];
+    return BSI_OK;
+}
+
+int launch(bsi_plan *p, CUfunction f, unsigned grid, unsigned block, size_t smem, void **args) {
+    if (grid == 0) return BSI_OK;
+    CU_CHECK(cuLaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, p->stream, args, nullptr));
+    ++p->launches;
+    return BSI_OK;
+}
+
+// ---- filter-node choice: a small host-side activity probe of the network ---------------------
+// (tuning only: the filter never decides a result, every filter pass is followed by a full
+//  compare.)  Nodes that keep toggling late in random trajectories discriminate states best.
+std::vector<int> choose_filter(const bsi::Model &m, int want) {
+    const int n = m.n;
+    want = std::min(want, n);
+    std::vector<uint8_t> x(n), y(n);
+    std::vector<long> toggles(n, 0);
+    std::mt19937_64 rng(0xB51u);
+    bool too_wide = false;
+    for (int i = 0; i < n; ++i) if (m.fn[i].k() > 20) too_wide = true;
+    const int n_traj = too_wide ? 0 : 48, n_steps = 192;
+    for (int tr = 0; tr < n_traj; ++tr) {
+        for (int i = 0; i < n; ++i) x[i] = (uint8_t)(rng() & 1);
+        for (int t = 0; t < n_steps; ++t) {
+            for (int i = 0; i < n; ++i) {
+                auto fx = m.fixed.find(i);
+                if (fx != m.fixed.end()) { y[i] = (uint8_t)fx->second; continue; }
+                size_t j = 0;
+                for (int v : m.fn[i].vars) j = (j << 1) | x[v];
+                y[i] = m.fn[i].tt[j];
+            }
+            if (t >= n_steps / 2)
+                for (int i = 0; i < n; ++i) toggles[i] += x[i] != y[i];
+            x.swap(y);
+        }
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return toggles[a] > toggles[b]; });
+    std::vector<int> f(order.begin(), order.begin() + want);
+    std::sort(f.begin(), f.end());
+    return f;
+}
+
+int compile_plan(bsi_plan *p) {
+    const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
+    std::vector<int> filter = choose_filter(p->m, f_nodes);
+    p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
+    if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
+    const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
+    p->source = bsi::generate_header(p->m, filter, p->block, min_blocks, p->info);
+    p->source += "\n#line 1 \"bsi_template.cuh\"\n";
+    p->source += bsi_template_src;
+
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, p->source.c_str(), "bsi_kernels.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(BSI_E_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+    r = nvrtcCompileProgram(prog, 4, opts);
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    p->log.assign(log_size ? log_size : 1, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, &p->log[0]);
+    while (!p->log.empty() && p->log.back() == '\0') p->log.pop_back();
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(BSI_E_NVRTC, "kernel specialisation failed (%s):\n%.3500s", nvrtcGetErrorString(r), p->log.c_str());
+    }
+    size_t cubin_size = 0;
+    r = nvrtcGetCUBINSize(prog, &cubin_size);
+    if (r != NVRTC_SUCCESS || cubin_size == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(BSI_E_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    p->cubin.resize(cubin_size);
+    nvrtcGetCUBIN(prog, p->cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return BSI_OK;
+}
+
+int load_plan(bsi_plan *p, int device) {
+    if (!cu().ok) return fail(BSI_E_CUDA, "%s", cu().why.c_str());
+    int count = 0;
+    CU_CHECK(cuDeviceGetCount(&count));
+    if (device < 0 || device >= count) return fail(BSI_E_CUDA, "device %d out of range (%d devices)", device, count);
+    p->device = device;
+    CU_CHECK(cuDeviceGet(&p->dev, device));
+    CU_CHECK(cuDevicePrimaryCtxRetain(&p->ctx, p->dev));
+    CtxGuard g(p);
+    int major = 0, minor = 0;
+    CU_CHECK(cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, p->dev));
+    CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
+    if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
+    CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
+    CU_CHECK(cuModuleLoadData(&p->mod, p->cubin.data()));
+    CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
+    p->stream = p->own_stream;
+    CU_CHECK(cuModuleGetFunction(&p->f_traj, p->mod, "bsi_trajectories"));
+    if (p->m.mode == BSI_MODE_ATTRACT) {
+        CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mod, "bsi_attract_dense"));
+        CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mod, "bsi_attract_queue"));
+        CU_CHECK(cuModuleGetFunction(&p->f_key, p->mod, "bsi_resolve_key"));
+        CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mod, "bsi_resolve_mu"));
+        CU_CHECK(cuModuleGetFunction(&p->f_export, p->mod, "bsi_table_export"));
+        CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mod, "bsi_table_merge"));
+        p->main_smem = (size_t)32 * p->block * (8 + 8 * p->m.kw);
+        if (p->main_smem > 48 * 1024) {
+            CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
+            CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
+        }
+        int a = 0, b = 0;
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_dense, p->block, p->main_smem));
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&b, p->f_queue, p->block, p->main_smem));
+        p->main_blocks_per_sm = std::max(1, std::min(a, b));
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_key, p->block, 0));
+        p->key_blocks_per_sm = std::max(1, a);
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_mu, p->block, 0));
+        p->mu_blocks_per_sm = std::max(1, a);
+        p->table_log2 = p->opts.table_log2_slots ? p->opts.table_log2_slots : 20;
+        if (p->table_log2 < 4 || p->table_log2 > 28) return fail(BSI_E_ARG, "table_log2_slots out of range");
+        const size_t slot_bytes = (size_t)8 * p->m.kw + 32;
+        int rc = ensure(p, p->table, slot_bytes << p->table_log2);
+        if (rc) return rc;
+        CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
+    }
+    if (p->m.mode == BSI_MODE_TARGET) CU_CHECK(cuModuleGetFunction(&p->f_target, p->mod, "bsi_target_main"));
+    int rc = ensure(p, p->ctr, sizeof(Counters));
+    if (rc) return rc;
+    CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    return BSI_OK;
+}
+
+int create_plan(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                const bsi_target_desc *target, const bsi_plan_opts *opts, int device, bsi_plan **out) {
+    if (!out) return fail(BSI_E_ARG, "null output pointer");
+    *out = nullptr;
+    if (mode < BSI_MODE_SIMULATE || mode > BSI_MODE_TARGET) return fail(BSI_E_ARG, "bad mode %d", mode);
+    bsi_plan *p = new bsi_plan();
+    if (opts) p->opts = *opts;
+    std::string err = bsi::load_model(network, space, mode, target, p->m);
+    if (!err.empty()) {
+        delete p;
+        bool unsup = err.find("not supported") != std::string::npos || err.find("unsupported") != std::string::npos;
+        return fail(unsup ? BSI_E_UNSUPPORTED : BSI_E_ARG, "%s", err.c_str());
+    }
+    int rc = compile_plan(p);
+    if (rc == BSI_OK && device >= 0) rc = load_plan(p, device);
+    if (rc != BSI_OK) {
+        std::string keep = g_err;
+        bsi_plan_destroy(p);
+        g_err = keep;
+        return rc;
+    }
+    *out = p;
+    return BSI_OK;
+}
+
+int need_device(bsi_plan *p, int mode) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    if (p->device < 0 || !p->mod) return fail(BSI_E_CUDA, "this plan was specialised without a device and cannot run (no CPU fallback)");
+    if (mode >= 0 && p->m.mode != mode) return fail(BSI_E_ARG, "plan was created for another mode");
+    return BSI_OK;
+}
+
+int read_counters(bsi_plan *p, Counters *c) {
+    CU_CHECK(cuMemcpyDtoHAsync(c, p->ctr.p, sizeof(Counters), p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    return BSI_OK;
+}
+
+struct Timer {
+    std::vector<std::pair<CUevent, CUevent>> main, resolve;
+    CUevent e0 = nullptr, e1 = nullptr;
+};
+
+int elapsed(CUevent a, CUevent b, double *ms) {
+    float f = 0;
+    CU_CHECK(cuEventElapsedTime(&f, a, b));
+    *ms += f;
+    return BSI_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int bsi_abi_version(void) { return BSI_ABI_VERSION; }
+const char *bsi_last_error(void) { return g_err.c_str(); }
+
+int bsi_device_count(int *count) {
+    if (!count) return fail(BSI_E_ARG, "null pointer");
+    *count = 0;
+    if (!cu().ok) return fail(BSI_E_CUDA, "%s", cu().why.c_str());
+    CU_CHECK(cuDeviceGetCount(count));
+    return BSI_OK;
+}
+
+int bsi_plan_create(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                    const bsi_target_desc *target, const bsi_plan_opts *opts, int device,
+                    bsi_plan **out) {
+    if (device < 0) return fail(BSI_E_ARG, "device must be >= 0 (use bsi_plan_create_offline to specialise without a GPU)");
+    return create_plan(network, space, mode, target, opts, device, out);
+}
+
+int bsi_plan_create_offline(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                            const bsi_target_desc *target, const bsi_plan_opts *opts, bsi_plan **out) {
+    return create_plan(network, space, mode, target, opts, -1, out);
+}
+
+void bsi_plan_destroy(bsi_plan *p) {
+    if (!p) return;
+    if (p->ctx && cu().ok) {
+        {
+            CtxGuard g(p);
+            if (p->stream) cu().p_cuStreamSynchronize(p->stream);
+            for (DevBuf *b : {&p->ctr, &p->table, &p->found_q, &p->retry_q[0], &p->retry_q[1], &p->scratch,
+                              &p->misc, &p->misc2, &p->misc3})
+                if (b->p) cu().p_cuMemFree(b->p);
+            for (CUevent e : p->events) cu().p_cuEventDestroy(e);
+            if (p->own_stream) cu().p_cuStreamDestroy(p->own_stream);
+            if (p->mod) cu().p_cuModuleUnload(p->mod);
+        }
+        cu().p_cuDevicePrimaryCtxRelease(p->dev);
+    }
+    delete p;
+}
+
+int bsi_plan_n_problems(const bsi_plan *p, uint64_t *n) {
+    if (!p || !n) return fail(BSI_E_ARG, "null pointer");
+    *n = p->m.n_problems;
+    return BSI_OK;
+}
+
+int bsi_plan_key_words(const bsi_plan *p, uint32_t *kw) {
+    if (!p || !kw) return fail(BSI_E_ARG, "null pointer");
+    *kw = (uint32_t)p->m.kw;
+    return BSI_OK;
+}
+
+int bsi_plan_set_stream(bsi_plan *p, void *cuda_stream) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    p->stream = cuda_stream ? (CUstream)cuda_stream : p->own_stream;
+    return BSI_OK;
+}
+
+const char *bsi_plan_source(const bsi_plan *p) { return p ? p->source.c_str() : ""; }
+const char *bsi_plan_build_log(const bsi_plan *p) { return p ? p->log.c_str() : ""; }
+
+int bsi_plan_cubin(const bsi_plan *p, const void **data, uint64_t *bytes) {
+    if (!p || !data || !bytes) return fail(BSI_E_ARG, "null pointer");
+    *data = p->cubin.data();
+    *bytes = p->cubin.size();
+    return BSI_OK;
+}
+
+int bsi_plan_op_counts(const bsi_plan *p, uint32_t *update_lop3, uint32_t *compare_lop3,
+                       uint32_t *filter_lop3) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    if (update_lop3) *update_lop3 = (uint32_t)p->info.update_lop3;
+    if (compare_lop3) *compare_lop3 = (uint32_t)p->info.compare_lop3;
+    if (filter_lop3) *filter_lop3 = (uint32_t)p->info.filter_lop3;
+    return BSI_OK;
+}
+
+int bsi_plan_launch_config(const bsi_plan *p, uint32_t *n_sms, uint32_t *block_threads,
+                           uint32_t *blocks_per_sm) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    if (n_sms) *n_sms = (uint32_t)p->n_sms;
+    if (block_threads) *block_threads = (uint32_t)p->block;
+    if (blocks_per_sm) *blocks_per_sm = (uint32_t)p->main_blocks_per_sm;
+    return BSI_OK;
+}
+
+int bsi_compile_only(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                     const bsi_target_desc *target, const bsi_plan_opts *opts,
+                     uint64_t *cubin_bytes, char *log, uint64_t log_cap) {
+    bsi_plan *p = nullptr;
+    int rc = create_plan(network, space, mode, target, opts, -1, &p);
+    if (log && log_cap) {
+        const std::string &src = rc == BSI_OK ? p->log : g_err;
+        snprintf(log, (size_t)log_cap, "%s", src.c_str());
+    }
+    if (rc == BSI_OK) {
+        if (cubin_bytes) *cubin_bytes = p->cubin.size();
+        bsi_plan_destroy(p);
+    }
+    return rc;
+}
+
+// ---- attract ------------------------------------------------------------------------------------
+int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                    uint64_t max_attractor_l, bsi_run_stats *stats) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (idx_begin > idx_end || idx_end > p->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    bsi_run_stats st{};
+    st.n_problems = idx_end - idx_begin;
+    const uint64_t lp = p->m.lp_origin;
+    if (st.n_problems == 0) { if (stats) *stats = st; return BSI_OK; }
+    if (max_t <= lp) {
+        // model.py:201: the loop body never runs; every problem stops at t = lp with no attractor
+        st.n_without = st.n_problems;
+        st.steps = st.n_problems * lp;
+        if (stats) *stats = st;
+        return BSI_OK;
+    }
+    const uint64_t T = max_t == BSI_INF ? BSI_INF : max_t - lp;     // horizon relative to lp
+    const uint64_t kMaxH = (uint64_t)1 << 30;
+    CtxGuard g(p);
+    p->events_used = 0;
+    const uint64_t launches0 = p->launches;
+    Timer tm;
+    if ((rc = get_event(p, &tm.e0)) || (rc = get_event(p, &tm.e1))) return rc;
+
+    const uint32_t chunk_log2 = p->opts.chunk_log2 ? p->opts.chunk_log2 : 26;
+    if (chunk_log2 < 5 || chunk_log2 > 34) return fail(BSI_E_ARG, "chunk_log2 out of range");
+    const uint64_t chunk = (uint64_t)1 << chunk_log2;
+    const size_t found_bytes = 16 + 16 * (size_t)p->m.kw;
+    const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
+    const size_t scratch_bytes = (size_t)main_grid * p->block * 3 * p->m.n * sizeof(uint32_t);
+    if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
+
+    CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
+    CU_CHECK(cuEventRecord(tm.e0, p->stream));
+
+    // chunks are aligned to word boundaries (32 problems)
+    uint64_t b = idx_begin;
+    while (b < idx_end) {
+        uint64_t e = std::min(idx_end, ((b >> 5) << 5) + chunk);
+        uint64_t n_lanes = e - b;
+        if ((rc = ensure(p, p->found_q, found_bytes * (n_lanes + 32)))) return rc;
+        uint64_t H = p->opts.first_horizon ? p->opts.first_horizon : 1024;
+        H = std::min(H, kMaxH);
+        int which = 0;
+        bool dense = true;
+        uint64_t n_in = n_lanes;
+        for (;;) {
+            if (H >= T) H = T;
+            const int final_round = H == T ? 1 : 0;
+            if (!final_round)
+                if ((rc = ensure(p, p->retry_q[which], sizeof(uint64_t) * (n_in + 32)))) return rc;
+            Sched sched = make_sched(H);
+            CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, kPerRoundBytes, p->stream));
+            CUevent m0, m1, r0, r1;
+            if ((rc = get_event(p, &m0)) || (rc = get_event(p, &m1)) || (rc = get_event(p, &r0)) ||
+                (rc = get_event(p, &r1)))
+                return rc;
+            CU_CHECK(cuEventRecord(m0, p->stream));
+            uint64_t stop_t = max_t;      // only used in the final round
+            CUdeviceptr retry_out = final_round ? 0 : p->retry_q[which].p;
+            if (dense) {
+                uint64_t word0 = b >> 5, n_words = ((e + 31) >> 5) - word0;
+                void *args[] = {&word0, &n_words, &b, &e, &sched, (void *)&final_round, &stop_t,
+                                &p->found_q.p, &retry_out, &p->scratch.p, &p->ctr.p};
+                unsigned grid = (unsigned)std::min<uint64_t>(main_grid, (n_words + p->block - 1) / p->block);
+                if ((rc = launch(p, p->f_dense, grid, p->block, p->main_smem, args))) return rc;
+            } else {
+                CUdeviceptr in_q = p->retry_q[which ^ 1].p;
+                uint64_t n_words = (n_in + 31) >> 5;
+                void *args[] = {&in_q, &n_in, &sched, (void *)&final_round, &stop_t, &p->found_q.p,
+                                &retry_out, &p->scratch.p, &p->ctr.p};
+                unsigned grid = (unsigned)std::min<uint64_t>(main_grid, (n_words + p->block - 1) / p->block);
+                if ((rc = launch(p, p->f_queue, grid, p->block, p->main_smem, args))) return rc;
+            }
+            CU_CHECK(cuEventRecord(m1, p->stream));
+            tm.main.push_back({m0, m1});
+            // resolution of the matched lanes: the kernels read the queue length on the device
+            CU_CHECK(cuEventRecord(r0, p->stream));
+            {
+                CUdeviceptr n_found_p = p->ctr.p + offsetof(Counters, n_found);
+                void *args_k[] = {&p->found_q.p, &n_found_p, &p->ctr.p};
+                unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
+                if ((rc = launch(p, p->f_key, grid_k, p->block, 0, args_k))) return rc;
+                uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
+                void *args_m[] = {&p->found_q.p, &n_found_p, &t_rel, &cap_l, &stop_cap, &p->table.p,
+                                  &p->table_log2, &p->ctr.p};
+                unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
+                if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
+            }
+            CU_CHECK(cuEventRecord(r1, p->stream));
+            tm.resolve.push_back({r0, r1});
+            ++st.rounds;
+            if (final_round) break;
+            Counters c;
+            if ((rc = read_counters(p, &c))) return rc;
+            if (c.n_retry == 0) break;
+            if (H >= kMaxH) return fail(BSI_E_UNSUPPORTED, "a trajectory did not close within 2^30 steps");
+            n_in = c.n_retry;
+            dense = false;
+            which ^= 1;
+            H = std::min(H * 4, kMaxH);
+        }
+        b = e;
+    }
+    CU_CHECK(cuEventRecord(tm.e1, p->stream));
+    Counters c;
+    if ((rc = read_counters(p, &c))) return rc;
+    CU_CHECK(cuEventSynchronize(tm.e1));
+    if (c.table_full) return fail(BSI_E_CAPACITY, "attractor table overflow (raise table_log2_slots)");
+    if (c.internal_error) return fail(BSI_E_CUDA, "internal invariant failed in bsi_resolve_mu");
+    st.n_found = c.n_accepted;
+    st.n_without = c.n_without;
+    st.steps = c.steps;
+    st.device_steps = c.device_steps;
+    st.launches = p->launches - launches0;
+    if ((rc = elapsed(tm.e0, tm.e1, &st.ms_total))) return rc;
+    for (auto &pr : tm.main) if ((rc = elapsed(pr.first, pr.second, &st.ms_main))) return rc;
+    for (auto &pr : tm.resolve) if ((rc = elapsed(pr.first, pr.second, &st.ms_resolve))) return rc;
+    if (st.n_found + st.n_without != st.n_problems)
+        return fail(BSI_E_CUDA, "internal: %llu found + %llu without != %llu problems",
+                    (unsigned long long)st.n_found, (unsigned long long)st.n_without,
+                    (unsigned long long)st.n_problems);
+    if (stats) *stats = st;
+    return BSI_OK;
+}
+
+int bsi_attract_table_clear(bsi_plan *p) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    CtxGuard g(p);
+    CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    return BSI_OK;
+}
+
+static int export_table(bsi_plan *p, CUdeviceptr out, uint64_t cap, uint64_t *n) {
+    int rc = ensure(p, p->misc, 256);
+    if (rc) return rc;
+    CU_CHECK(cuMemsetD8Async(p->misc.p, 0, 8, p->stream));
+    if (out && cap) CU_CHECK(cuMemsetD8Async(out, 0, cap * sizeof(bsi_attractor_rec), p->stream));
+    void *args[] = {&p->table.p, &p->table_log2, &out, &cap, &p->misc.p};
+    if ((rc = launch(p, p->f_export, (unsigned)(p->n_sms * 4), 256, 0, args))) return rc;
+    uint64_t count = 0;
+    CU_CHECK(cuMemcpyDtoHAsync(&count, p->misc.p, 8, p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    if (n) *n = count;
+    return BSI_OK;
+}
+
+int bsi_attract_table_count(bsi_plan *p, uint64_t *n) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    CtxGuard g(p);
+    return export_table(p, 0, 0, n);
+}
+
+int bsi_attract_table_read(bsi_plan *p, bsi_attractor_rec *out, uint64_t cap, uint64_t *n) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    CtxGuard g(p);
+    if ((rc = ensure(p, p->misc2, std::max<uint64_t>(cap, 1) * sizeof(bsi_attractor_rec)))) return rc;
+    uint64_t count = 0;
+    if ((rc = export_table(p, p->misc2.p, cap, &count))) return rc;
+    if (n) *n = count;
+    if (count > cap) return fail(BSI_E_CAPACITY, "attractor table holds %llu records, buffer %llu",
+                                 (unsigned long long)count, (unsigned long long)cap);
+    if (count && out) {
+        CU_CHECK(cuMemcpyDtoHAsync(out, p->misc2.p, count * sizeof(bsi_attractor_rec), p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+    }
+    return BSI_OK;
+}
+
+int bsi_attract_table_export_device(bsi_plan *p, void *dev_out, uint64_t cap, uint64_t *n) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (!dev_out) return fail(BSI_E_ARG, "null device buffer");
+    CtxGuard g(p);
+    uint64_t count = 0;
+    if ((rc = export_table(p, (CUdeviceptr)dev_out, cap, &count))) return rc;
+    if (n) *n = count;
+    if (count > cap) return fail(BSI_E_CAPACITY, "attractor table holds %llu records, buffer %llu",
+                                 (unsigned long long)count, (unsigned long long)cap);
+    return BSI_OK;
+}
+
+int bsi_attract_table_merge_device(bsi_plan *p, const void *dev_records, uint64_t n) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (n == 0) return BSI_OK;
+    if (!dev_records) return fail(BSI_E_ARG, "null device buffer");
+    CtxGuard g(p);
+    CUdeviceptr recs = (CUdeviceptr)dev_records;
+    void *args[] = {&p->table.p, &p->table_log2, &recs, &n, &p->ctr.p};
+    CU_CHECK(cuMemsetD8Async(p->ctr.p + offsetof(Counters, table_full), 0, 8, p->stream));
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)p->n_sms * 4);
+    if ((rc = launch(p, p->f_merge, grid, 256, 0, args))) return rc;
+    Counters c;
+    if ((rc = read_counters(p, &c))) return rc;
+    if (c.table_full) return fail(BSI_E_CAPACITY, "attractor table overflow (raise table_log2_slots)");
+    return BSI_OK;
+}
+
+// ---- trajectories (simulate, orbits) --------------------------------------------------------------
+static int run_trajectories(bsi_plan *p, uint64_t idx_begin, const uint64_t *indices,
+                            const uint64_t *codes, uint64_t n, uint64_t n_steps, uint64_t *out,
+                            bsi_run_stats *stats) {
+    int rc;
+    const uint64_t kw = (uint64_t)p->m.kw;
+    if (n_steps >= ((uint64_t)1 << 40)) return fail(BSI_E_ARG, "max_t too large for an explicit trajectory");
+    const uint64_t per_lane = (n_steps + 1) * kw * sizeof(uint64_t);
+    uint64_t lanes_per_call = std::max<uint64_t>(32, (((uint64_t)1 << 30) / per_lane) & ~(uint64_t)31);
+    bsi_run_stats st{};
+    st.n_problems = n;
+    p->events_used = 0;
+    const uint64_t launches0 = p->launches;
+    CUevent e0, e1;
+    if ((rc = get_event(p, &e0)) || (rc = get_event(p, &e1))) return rc;
+    CU_CHECK(cuEventRecord(e0, p->stream));
+    for (uint64_t done = 0; done < n;) {
+        uint64_t m = std::min(lanes_per_call, n - done);
+        if ((rc = ensure(p, p->misc, m * per_lane))) return rc;
+        CUdeviceptr d_idx = 0, d_codes = 0;
+        if (indices) {
+            if ((rc = ensure(p, p->misc2, m * 8))) return rc;
+            CU_CHECK(cuMemcpyHtoDAsync(p->misc2.p, indices + done, m * 8, p->stream));
+            d_idx = p->misc2.p;
+        }
+        if (codes) {
+            if ((rc = ensure(p, p->misc3, m * 8 * kw))) return rc;
+            CU_CHECK(cuMemcpyHtoDAsync(p->misc3.p, codes + done * kw, m * 8 * kw, p->stream));
+            d_codes = p->misc3.p;
+        }
+        uint64_t first = idx_begin + done;
+        void *args[] = {&first, &d_idx, &d_codes, &m, &n_steps, &p->misc.p};
+        uint64_t n_words = (m + 31) >> 5;
+        if ((rc = launch(p, p->f_traj, (unsigned)((n_words + p->block - 1) / p->block), p->block, 0, args))) return rc;
+        CU_CHECK(cuMemcpyDtoHAsync(out + done * (n_steps + 1) * kw, p->misc.p, m * per_lane, p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+        done += m;
+    }
+    CU_CHECK(cuEventRecord(e1, p->stream));
+    CU_CHECK(cuEventSynchronize(e1));
+    if ((rc = elapsed(e0, e1, &st.ms_total))) return rc;
+    st.ms_main = st.ms_total;
+    st.steps = n * n_steps;
+    st.device_steps = ((n + 31) >> 5) * n_steps;
+    st.launches = p->launches - launches0;
+    st.n_found = n;
+    if (stats) *stats = st;
+    return BSI_OK;
+}
+
+int bsi_simulate_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                     uint64_t *states_out, bsi_run_stats *stats) {
+    int rc = need_device(p, -1);
+    if (rc) return rc;
+    if (idx_begin > idx_end || idx_end > p->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    if (!states_out && idx_end > idx_begin) return fail(BSI_E_ARG, "null output buffer");
+    if (max_t < p->m.lp_max) return fail(BSI_E_ARG, "simulate: max_t is smaller than the last perturbation time");
+    CtxGuard g(p);
+    return run_trajectories(p, idx_begin, nullptr, nullptr, idx_end - idx_begin, max_t, states_out, stats);
+}
+
+int bsi_simulate_list(bsi_plan *p, const uint64_t *indices, uint64_t n, uint64_t max_t,
+                      uint64_t *states_out, bsi_run_stats *stats) {
+    int rc = need_device(p, -1);
+    if (rc) return rc;
+    if (n && (!indices || !states_out)) return fail(BSI_E_ARG, "null buffer");
+    for (uint64_t i = 0; i < n; ++i)
+        if (indices[i] >= p->m.n_problems) return fail(BSI_E_ARG, "problem index out of range");
+    CtxGuard g(p);
+    return run_trajectories(p, 0, indices, nullptr, n, max_t, states_out, stats);
+}
+
+int bsi_attractor_states(bsi_plan *p, const uint64_t *key, uint64_t lambda, uint64_t *out) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (!key || !out || lambda == 0) return fail(BSI_E_ARG, "bad arguments");
+    CtxGuard g(p);
+    return run_trajectories(p, 0, nullptr, key, 1, lambda - 1, out, nullptr);
+}
+
+// ---- target ---------------------------------------------------------------------------------------
+int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                   uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,
+                   bsi_run_stats *stats) {
+    int rc = need_device(p, BSI_MODE_TARGET);
+    if (rc) return rc;
+    if (idx_begin > idx_end || idx_end > p->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    if (cap && (!hit_index || !hit_t)) return fail(BSI_E_ARG, "null hit buffers");
+    CtxGuard g(p);
+    bsi_run_stats st{};
+    st.n_problems = idx_end - idx_begin;
+    p->events_used = 0;
+    const uint64_t launches0 = p->launches;
+    CUevent e0, e1;
+    if ((rc = get_event(p, &e0)) || (rc = get_event(p, &e1))) return rc;
+    CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
+    CU_CHECK(cuEventRecord(e0, p->stream));
+    const uint32_t chunk_log2 = p->opts.chunk_log2 ? p->opts.chunk_log2 : 26;
+    const uint64_t chunk = (uint64_t)1 << chunk_log2;
+    const uint64_t kMaxH = (uint64_t)1 << 30;
+    uint64_t written = 0, total_hits = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> hits;
+    std::vector<uint64_t> hi, ht;
+    for (uint64_t b = idx_begin; b < idx_end;) {
+        uint64_t e = std::min(idx_end, b + chunk);
+        uint64_t n_lanes = e - b;
+        if ((rc = ensure(p, p->misc, 8 * n_lanes)) || (rc = ensure(p, p->misc2, 8 * n_lanes))) return rc;
+        hits.clear();
+        uint64_t T = max_t == BSI_INF ? std::max<uint64_t>(1024, 2 * p->m.lp_max) : max_t;
+        uint64_t n_in = n_lanes;
+        int which = 0;
+        bool dense = true;
+        for (;;) {
+            int check_closure = (max_t == BSI_INF || T < max_t) ? 1 : 0;
+            if (check_closure) {
+                if ((rc = ensure(p, p->retry_q[which], 8 * n_in)) || (rc = ensure(p, p->found_q, 8 * n_in))) return rc;
+            }
+            // per round: hits of this round start at 0
+            CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, kPerRoundBytes, p->stream));
+            CU_CHECK(cuMemsetD8Async(p->ctr.p + offsetof(Counters, n_hits), 0, 8, p->stream));
+            CUdeviceptr in_q = dense ? 0 : p->retry_q[which ^ 1].p;
+            CUdeviceptr retry_out = check_closure ? p->retry_q[which].p : 0;
+            CUdeviceptr closed_out = check_closure ? p->found_q.p : 0;
+            uint64_t hit_cap = n_lanes;
+            void *args[] = {&b, &in_q, &n_in, &T, &check_closure, &p->misc.p, &p->misc2.p, &hit_cap,
+                            &retry_out, &closed_out, &p->ctr.p};
+            uint64_t n_words = (n_in + 31) >> 5;
+            if ((rc = launch(p, p->f_target, (unsigned)((n_words + p->block - 1) / p->block), p->block, 0, args))) return rc;
+            ++st.rounds;
+            Counters c;
+            if ((rc = read_counters(p, &c))) return rc;
+            if (c.n_hits) {
+                hi.resize(c.n_hits);
+                ht.resize(c.n_hits);
+                CU_CHECK(cuMemcpyDtoHAsync(hi.data(), p->misc.p, 8 * c.n_hits, p->stream));
+                CU_CHECK(cuMemcpyDtoHAsync(ht.data(), p->misc2.p, 8 * c.n_hits, p->stream));
+                CU_CHECK(cuStreamSynchronize(p->stream));
+                for (uint64_t i = 0; i < c.n_hits; ++i) hits.push_back({hi[i], ht[i]});
+            }
+            st.n_without += c.n_found;     // closed without a hit
+            if (!check_closure || c.n_retry == 0) break;
+            if (T >= kMaxH) return fail(BSI_E_UNSUPPORTED, "a trajectory did not close within 2^30 steps");
+            n_in = c.n_retry;
+            dense = false;
+            which ^= 1;
+            T = std::min(T * 4, kMaxH);
+            if (max_t != BSI_INF && T > max_t) T = max_t;
+        }
+        std::sort(hits.begin(), hits.end());
+        total_hits += hits.size();
+        for (auto &h : hits) {
+            if (written >= cap) break;
+            hit_index[written] = h.first;
+            hit_t[written] = h.second;
+            ++written;
+        }
+        b = e;
+    }
+    CU_CHECK(cuEventRecord(e1, p->stream));
+    Counters c;
+    if ((rc = read_counters(p, &c))) return rc;
+    CU_CHECK(cuEventSynchronize(e1));
+    if ((rc = elapsed(e0, e1, &st.ms_total))) return rc;
+    st.ms_main = st.ms_total;
+    st.n_found = total_hits;
+    st.n_without += c.n_without;
+    st.steps = c.steps;
+    st.device_steps = c.device_steps;
+    st.launches = p->launches - launches0;
+    if (n_hits) *n_hits = written;
+    if (stats) *stats = st;
+    return BSI_OK;
+}
+
+// ---- integer-logic roofline microbenchmark --------------------------------------------------------
+static const char *kPeakSrc = R"BSIRAW(
+typedef unsigned int u32;
+// 16 independent chains per thread, each link one lop3.b32 (LUT 0x96 = a ^ b ^ c).
+extern "C" __global__ void __launch_bounds__(256) bsi_lop3_peak(u32 *out, u32 iters, u32 seed) {
+    u32 r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = seed * (i + 1) + threadIdx.x;
+    u32 k1 = seed ^ 0x9E3779B9u, k2 = seed + blockIdx.x;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(k1), "r"(k2));
+        }
+    }
+    u32 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= r[i];
+    if (acc == 0x12345678u) out[0] = acc;
+}
+)BSIRAW";
+
+int bsi_measure_lop3_peak(int device, double *lop3_per_s, double *sm_clock_mhz, int *n_sms) {
+    if (!cu().ok) return fail(BSI_E_CUDA, "%s", cu().why.c_str());
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, kPeakSrc, "bsi_peak.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(BSI_E_NVRTC, "nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo"};
+    if (nvrtcCompileProgram(prog, 2, opts) != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(BSI_E_NVRTC, "peak kernel failed to compile");
+    }
+    size_t sz = 0;
+    nvrtcGetCUBINSize(prog, &sz);
+    std::vector<char> cubin(sz);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    bsi_plan tmp;
+    int count = 0;
+    CU_CHECK(cuDeviceGetCount(&count));
+    if (device < 0 || device >= count) return fail(BSI_E_CUDA, "device out of range");
+    CU_CHECK(cuDeviceGet(&tmp.dev, device));
+    CU_CHECK(cuDevicePrimaryCtxRetain(&tmp.ctx, tmp.dev));
+    int rc = BSI_OK;
+    {
+        CtxGuard g(&tmp);
+        CUmodule mod = nullptr;
+        CUfunction f = nullptr;
+        CUstream s = nullptr;
+        CUevent e0 = nullptr, e1 = nullptr;
+        CUdeviceptr out = 0;
+        int sms = 0, clk_khz = 0;
+        auto body = [&]() -> int {
+            CU_CHECK(cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, tmp.dev));
+            CU_CHECK(cuDeviceGetAttribute(&clk_khz, CU_DEVICE_ATTRIBUTE_CLOCK_RATE, tmp.dev));
+            CU_CHECK(cuModuleLoadData(&mod, cubin.data()));
+            CU_CHECK(cuModuleGetFunction(&f, mod, "bsi_lop3_peak"));
+            CU_CHECK(cuStreamCreate(&s, CU_STREAM_NON_BLOCKING));
+            CU_CHECK(cuEventCreate(&e0, CU_EVENT_DEFAULT));
+            CU_CHECK(cuEventCreate(&e1, CU_EVENT_DEFAULT));
+            CU_CHECK(cuMemAlloc(&out, 256));
+            uint32_t iters = 20000, seed = 12345;
+            unsigned grid = (unsigned)sms * 8;
+            void *args[] = {&out, &iters, &seed};
+            double best = 0;
+            for (int rep = 0; rep < 5; ++rep) {
+                CU_CHECK(cuEventRecord(e0, s));
+                CU_CHECK(cuLaunchKernel(f, grid, 1, 1, 256, 1, 1, 0, s, args, nullptr));
+                CU_CHECK(cuEventRecord(e1, s));
+                CU_CHECK(cuEventSynchronize(e1));
+                float ms = 0;
+                CU_CHECK(cuEventElapsedTime(&ms, e0, e1));
+                double ops = (double)grid * 256.0 * iters * 8.0 * 16.0;
+                if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+            }
+            if (lop3_per_s) *lop3_per_s = best;
+            if (n_sms) *n_sms = sms;
+            // clock implied by 64 lop3 / clk / SM (alu pipe: 16 lanes x 4 sub-partitions)
+            if (sm_clock_mhz) *sm_clock_mhz = best / (64.0 * sms) / 1e6;
+            return BSI_OK;
+        };
+        rc = body();
+        if (out) cu().p_cuMemFree(out);
+        if (e0) cu().p_cuEventDestroy(e0);
+        if (e1) cu().p_cuEventDestroy(e1);
+        if (s) cu().p_cuStreamDestroy(s);
+        if (mod) cu().p_cuModuleUnload(mod);
+    }
+    cu().p_cuDevicePrimaryCtxRelease(tmp.dev);
+    tmp.ctx = nullptr;
+    return rc;
+}
+
+}  // extern "C"

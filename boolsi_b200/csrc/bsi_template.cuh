@@ -1,0 +1,891 @@
+// Hand-written sm_100a kernel template of libbsi.  Compiled at plan-creation time by NVRTC after
+// the per-network macro header (bsi_codegen.hpp) has been prepended.
+//
+// Layout: trajectories are bit-sliced, 32 per 32-bit word ("lanes"), one register word per
+// network node; one thread owns one word at a time.  A synchronous step (reference
+// model.py:16-73) is BSI_UPDATE: one lop3.b32 per node with <= 3 inputs, a Shannon tree of lop3
+// for wider rules, constants and AND/OR masks for fixed nodes and perturbations.  State never
+// leaves registers; HBM sees only result records.
+//
+// attract (reference model.py:152-236 + attract.py:262-302, default "storing all states" mode).
+// The reference stops a trajectory at the first repeated state, t = mu + lambda (relative to the
+// last perturbation time lp), provided that is <= T = max_t - lp.  Here, store-free:
+//
+//   bsi_attract_main   one forward pass per word with up to three live CHECKPOINTS.  A lane whose
+//       state equals a checkpoint taken at time c is on its cycle, c >= mu, and because every
+//       later state is compared the first such match is at time c + lambda: lambda is exact.
+//       Checkpoint times for a horizon H: powers of two while they are < H/3 (early detection,
+//       Brent style, all in slot 0), then ceil(H/3), ceil(2H/3), H in slots 0, 1, 2.  A lane with
+//       c_(i-1) < mu <= c_i and mu + lambda <= H is matched by time c_i + lambda < H + gap, so
+//       running to H + max gap - 1 PROVES "mu + lambda > H" for every lane still unmatched.
+//       The per-step compare is a FILTER over a few nodes held in registers; only when some lane
+//       passes the filter is the full state compared against the checkpoint kept in an
+//       L2-resident scratch (persistent grid: scratch is sized by resident threads).
+//   bsi_resolve_key    canonical key = minimum state code over the cycle (model.py:140-149,
+//       attract.py:296) by a bit-sliced lexicographic-minimum walk of the cycle.
+//   bsi_resolve_mu     exact mu by walking x_j (from the problem index) in lock-step with the
+//       periodic extension of the cycle; then acceptance (mu + lambda <= T, lambda <=
+//       max_attractor_l, attract.py:294) and aggregation into the device attractor table.
+
+typedef unsigned char u8;
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+template <int LUT>
+__device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
+    u32 d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
+#define BSI_MAX_CK 72
+
+struct BsiCounters {
+    // reset before every round
+    u64 next_word;      // work counter of the persistent trajectory kernel
+    u64 next_word2;     // work counter of bsi_resolve_key
+    u64 next_word3;     // work counter of bsi_resolve_mu
+    u64 n_found;        // entries in the found queue (target: closed queue)
+    u64 n_retry;        // entries in the retry queue
+    // accumulated over a run
+    u64 n_without;      // lanes proven to have no attractor within the caps
+    u64 n_accepted;     // lanes whose attractor went into the table
+    u64 steps;          // sum of reference stop times (model.py:235) of finished lanes
+    u64 device_steps;   // word-steps executed by the trajectory kernels
+    u64 table_full;     // set when the attractor table overflowed
+    u64 n_hits;         // target: number of hits
+    u64 internal_error; // set when an invariant of the resolution kernels failed
+    u64 pad[4];
+};
+
+struct BsiSched {       // checkpoint schedule of one detection round (times relative to lp)
+    u32 n_ck;
+    u32 end;            // last compared time
+    u32 ck_time[BSI_MAX_CK];
+    u32 ck_slot[BSI_MAX_CK];
+};
+
+struct BsiFound {       // one lane that matched a checkpoint
+    u64 idx;            // problem index
+    u64 y[BSI_KW];      // the matched state (on the cycle), state code words
+    u64 key[BSI_KW];    // canonical key, filled by bsi_resolve_key
+    u32 lam;            // cycle length
+    u32 c;              // time of the matched checkpoint (>= mu), relative to lp
+};
+
+struct BsiSlot {
+    u64 key[BSI_KW];
+    u64 n, s1, s2;
+    u32 lam;
+    u32 flag;           // 0 empty, 1 being written, 2 ready
+};
+
+struct BsiRec {         // == bsi_attractor_rec (include/bsi.h)
+    u64 key[4];
+    u64 n, s1, s2, lam;
+};
+
+#define BSI_DECL_ONE(P, i) u32 P##i;
+#define BSI_DECL_A(i) BSI_DECL_ONE(a, i)
+#define BSI_DECL_B(i) BSI_DECL_ONE(b, i)
+#define BSI_DECL_C(i) BSI_DECL_ONE(c, i)
+#define BSI_DECL_K0(i) BSI_DECL_ONE(k0_, i)
+#define BSI_DECL_K1(i) BSI_DECL_ONE(k1_, i)
+#define BSI_DECL_K2(i) BSI_DECL_ONE(k2_, i)
+#define BSI_ZERO_A(i) a##i = 0u;
+#define BSI_ZERO_B(i) b##i = 0u;
+#define BSI_COPY_AB(i) a##i = b##i;
+#define BSI_COPY_BA(i) b##i = a##i;
+#define BSI_COPY_CA(i) c##i = a##i;
+#define BSI_SAVE_K0(i) k0_##i = a##i;
+#define BSI_SAVE_K1(i) k1_##i = a##i;
+#define BSI_SAVE_K2(i) k2_##i = a##i;
+#define BSI_ZERO_K(i) k0_##i = 0u; k1_##i = 0u; k2_##i = 0u;
+
+// lane masks of per-lane fixed nodes / perturbation variations (simulate and target only)
+#define BSI_DECL_FIXVAR(i) u32 fm##i = 0u, fv##i = 0u;
+#define BSI_DECL_PVAR(q) u32 pm##q = 0u, pv##q = 0u;
+
+__device__ __forceinline__ u64 bsi_hash_key(const u64 *k) {
+    u64 h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < BSI_KW; ++i) {
+        h ^= k[i];
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
+// Adds (n, s1, s2) for `key` to the open-addressing table (the replacement for the ZODB store and
+// the Welford/Chan merges of reference attract.py:35-45, 405-455: integer sums are exact and
+// order-independent).
+__device__ __noinline__ void bsi_table_add(BsiSlot *table, u32 log2_slots, const u64 *key, u64 n,
+                                           u64 s1, u64 s2, u32 lam, BsiCounters *ctr) {
+    const u64 mask = ((u64)1 << log2_slots) - 1;
+    u64 pos = bsi_hash_key(key) & mask;
+    for (u64 probe = 0; probe <= mask; ++probe, pos = (pos + 1) & mask) {
+        BsiSlot *s = table + pos;
+        u32 f = *((volatile u32 *)&s->flag);
+        if (f == 0u) {
+            u32 old = atomicCAS(&s->flag, 0u, 1u);
+            if (old == 0u) {
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) s->key[i] = key[i];
+                s->lam = lam;
+                __threadfence();
+                atomicExch(&s->flag, 2u);
+                f = 2u;
+            } else {
+                f = old;
+            }
+        }
+        while (f == 1u) f = *((volatile u32 *)&s->flag);
+        __threadfence();
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) same = same && (((volatile u64 *)s->key)[i] == key[i]);
+        if (same) {
+            atomicAdd(&s->n, n);
+            atomicAdd(&s->s1, s1);
+            atomicAdd(&s->s2, s2);
+            return;
+        }
+    }
+    atomicExch(&ctr->table_full, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+
+// lanes of word W (problems 32W .. 32W+31) that fall into [idx_begin, idx_end)
+__device__ __forceinline__ u32 bsi_valid_mask(u64 W, u64 idx_begin, u64 idx_end) {
+    u64 base = W << 5;
+    u32 v = 0xFFFFFFFFu;
+    if (base < idx_begin) {
+        u64 skip = idx_begin - base;
+        v = skip >= 32 ? 0u : (0xFFFFFFFFu << (u32)skip);
+    }
+    if (base + 32 > idx_end) {
+        u64 keep = idx_end > base ? idx_end - base : 0;
+        v &= keep >= 32 ? 0xFFFFFFFFu : ((1u << (u32)keep) - 1u);
+    }
+    return v;
+}
+
+// each warp takes 32 consecutive words from a global counter; returns this thread's word
+__device__ __forceinline__ u64 bsi_grab_word(u64 *counter) {
+    u64 base = 0;
+    if ((threadIdx.x & 31u) == 0u) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + (threadIdx.x & 31u);
+}
+
+// warp-aggregated reservation of `n` queue entries per thread; returns this thread's first index
+__device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
+    const u32 lane = threadIdx.x & 31u;
+    u32 incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += t;
+    }
+    const u32 tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    u64 base = 0;
+    if (lane == 31u && tot) base = atomicAdd(counter, (u64)tot);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    return base + (incl - n);
+}
+
+// perturbation prefix: LP steps from t = 0, perturbations overriding at their time
+// (reference model.py:76-128).  Ends with the state at time LP in a*.
+#define BSI_PREFIX(LP)                                                              \
+    {                                                                               \
+        u64 t_ = 1;                                                                 \
+        for (; t_ + 1 <= (LP); t_ += 2) {                                           \
+            BSI_UPDATE(b, a) BSI_PERTURB(b, t_)                                     \
+            BSI_UPDATE(a, b) BSI_PERTURB(a, (t_ + 1))                               \
+        }                                                                           \
+        if (t_ <= (LP)) { BSI_UPDATE(b, a) BSI_PERTURB(b, t_) BSI_FOR_NODES(BSI_COPY_AB) } \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// attract
+// ---------------------------------------------------------------------------------------------
+#if BSI_MODE == 1
+
+// dynamic shared memory of the main kernel: per (lane, thread) detection records
+//   u32 lam[32][BLOCK], u32 c[32][BLOCK], u64 y[KW][32][BLOCK]
+extern __shared__ __align__(16) unsigned char bsi_smem[];
+
+// full compare of a state held in local memory with a checkpoint in the scratch: lanes of
+// `cand` whose N words all agree
+__device__ __noinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 sstride, u32 cand) {
+    u32 acc = ~cand;
+    for (int i = 0; i < BSI_N && acc != 0xFFFFFFFFu; ++i) acc |= xs[i] ^ ck[(u64)i * sstride];
+    return ~acc;
+}
+
+// detection record of the lanes in m: cycle length, checkpoint time and the matched state code
+__device__ __noinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
+                                        u64 *y_s) {
+    const u32 tid = threadIdx.x;
+    while (m) {
+        const u32 l = __ffs(m) - 1;
+        m &= m - 1;
+        u64 code[BSI_KW];
+#pragma unroll
+        for (int k = 0; k < BSI_KW; ++k) code[k] = 0ull;
+        for (int i = 0; i < BSI_N; ++i) code[i >> 6] |= (u64)((xs[i] >> l) & 1u) << (i & 63);
+        lam_s[l * BSI_BLOCK + tid] = lam;
+        c_s[l * BSI_BLOCK + tid] = c;
+#pragma unroll
+        for (int k = 0; k < BSI_KW; ++k) y_s[(k * 32 + l) * BSI_BLOCK + tid] = code[k];
+    }
+}
+
+// DENSE: words of the contiguous index range [idx_begin, idx_end), word0 = idx_begin >> 5.
+// otherwise: word w = lanes 32w .. 32w+31 of the retry queue `in_queue`.
+template <bool DENSE>
+__device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end,
+                                              const u64 *__restrict__ in_queue, u64 n_in,
+                                              const BsiSched &sched, int final_round, u64 stop_t,
+                                              BsiFound *found_q, u64 *retry_q, u32 *scratch,
+                                              BsiCounters *ctr) {
+    u32 *lam_s = (u32 *)bsi_smem;
+    u32 *c_s = lam_s + 32 * BSI_BLOCK;
+    u64 *y_s = (u64 *)(c_s + 32 * BSI_BLOCK);
+    const u32 tid = threadIdx.x;
+    const u64 sstride = (u64)gridDim.x * BSI_BLOCK;
+    u32 *const my_scratch = scratch + ((u64)blockIdx.x * BSI_BLOCK + tid);
+    u64 dev_steps = 0, n_without = 0, ref_steps = 0;
+
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        const bool active = w < n_words;
+        BSI_FOR_NODES(BSI_DECL_A)
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_FOR_FILTER(BSI_DECL_K0)
+        BSI_FOR_FILTER(BSI_DECL_K1)
+        BSI_FOR_FILTER(BSI_DECL_K2)
+        u32 valid = 0u, F = 0u, alive = 0u;
+
+        if (active) {
+            // ---- x_0 .. x_lp ----------------------------------------------------------------
+            if (DENSE) {
+                const u64 W = word0 + w;
+                valid = bsi_valid_mask(W, idx_begin, idx_end);
+                BSI_INIT_DENSE(a, W)
+            } else {
+                BSI_FOR_NODES(BSI_ZERO_A)
+                for (u32 l = 0; l < 32; ++l) {
+                    u64 q = (w << 5) + l;
+                    if (q < n_in) {
+                        u64 c_[BSI_KW];
+                        u64 lp_lane_ = 0;
+                        BSI_LANE_SETUP(l, in_queue[q], c_)
+                        (void)lp_lane_;
+                        BSI_INSERT(a, l, c_)
+                        valid |= 1u << l;
+                    }
+                }
+            }
+            BSI_PREFIX(BSI_LP_ORIGIN)
+            BSI_FOR_FILTER(BSI_ZERO_K)
+
+            alive = valid;
+            u32 j = 0, ci = 0, armed = 0;
+            u32 st0 = 0, st1 = 0, st2 = 0;       // checkpoint time held by each slot
+
+            // Cold path, taken when some lane passes a filter: the state goes to local memory and
+            // two out-of-line functions do the full compare against the checkpoint scratch and
+            // record the matching lanes, so that the hot loop's register allocation only sees
+            // the state words, the filter words and a handful of scalars.
+#define BSI_FULL(XS, J, S, ST, ACC)                                                  \
+    {                                                                                \
+        u32 cand_ = ~(ACC) & alive;                                                  \
+        if (cand_) {                                                                 \
+            u32 m_ = bsi_slow_match(XS, my_scratch + (u64)(S) * BSI_N * sstride, sstride, cand_); \
+            if (m_) {                                                                \
+                F |= m_;                                                             \
+                alive &= ~m_;                                                        \
+                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s);               \
+            }                                                                        \
+        }                                                                            \
+    }
+#define BSI_CMP1(X, J)                                                               \
+    {                                                                                \
+        u32 p0 = ~alive, q0 = 0u;                                                    \
+        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
+        p0 |= q0;                                                                    \
+        if (p0 != 0xFFFFFFFFu) {                                                     \
+            u32 xs_[BSI_N];                                                          \
+            BSI_DUMP(X, xs_)                                                         \
+            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+        }                                                                            \
+    }
+#define BSI_CMP2(X, J)                                                               \
+    {                                                                                \
+        u32 p0 = ~alive, q0 = 0u, p1 = p0, q1 = 0u;                                  \
+        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
+        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
+        p0 |= q0;                                                                    \
+        p1 |= q1;                                                                    \
+        if ((p0 & p1) != 0xFFFFFFFFu) {                                              \
+            u32 xs_[BSI_N];                                                          \
+            BSI_DUMP(X, xs_)                                                         \
+            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+            BSI_FULL(xs_, J, 1, st1, p1)                                             \
+        }                                                                            \
+    }
+#define BSI_CMP3(X, J)                                                               \
+    {                                                                                \
+        u32 p0 = ~alive, q0 = 0u, p1 = p0, q1 = 0u, p2 = p0, q2 = 0u;                \
+        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
+        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
+        BSI_CMP_FILTER(p2, q2, X, k2_)                                               \
+        p0 |= q0;                                                                    \
+        p1 |= q1;                                                                    \
+        p2 |= q2;                                                                    \
+        if (bsi_lop3<0x80>(p0, p1, p2) != 0xFFFFFFFFu) {                             \
+            u32 xs_[BSI_N];                                                          \
+            BSI_DUMP(X, xs_)                                                         \
+            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+            BSI_FULL(xs_, J, 1, st1, p1)                                             \
+            BSI_FULL(xs_, J, 2, st2, p2)                                             \
+        }                                                                            \
+    }
+#define BSI_CMP0(X, J) {}
+            // n_ steps from time j, comparing every new state with the armed slots
+#define BSI_SEGMENT(CMP)                                                             \
+    {                                                                                \
+        u32 n_ = seg_end - j;                                                        \
+        for (; n_ >= 2u && alive; n_ -= 2u, j += 2u) {                               \
+            BSI_UPDATE(b, a)                                                         \
+            CMP(b, j + 1u)                                                           \
+            BSI_UPDATE(a, b)                                                         \
+            CMP(a, j + 2u)                                                           \
+        }                                                                            \
+        if (n_ == 1u && alive) {                                                     \
+            BSI_UPDATE(b, a)                                                         \
+            CMP(b, j + 1u)                                                           \
+            BSI_FOR_NODES(BSI_COPY_AB)                                               \
+            j += 1u;                                                                 \
+            n_ = 0u;                                                                 \
+        }                                                                            \
+        dev_steps += (seg_end - j0_) - n_;                                           \
+    }
+            while (alive) {
+                // checkpoint due at time j: state a (already compared) goes into its slot
+                if (ci < sched.n_ck && sched.ck_time[ci] == j) {
+                    const u32 s = sched.ck_slot[ci];
+                    u32 *p_ = my_scratch + (u64)s * BSI_N * sstride;
+                    BSI_STORE_ALL(a, p_, sstride)
+                    if (s == 0u) { BSI_FOR_FILTER(BSI_SAVE_K0) st0 = j; }
+                    else if (s == 1u) { BSI_FOR_FILTER(BSI_SAVE_K1) st1 = j; }
+                    else { BSI_FOR_FILTER(BSI_SAVE_K2) st2 = j; }
+                    if (armed < s + 1u) armed = s + 1u;
+                    ++ci;
+                    continue;
+                }
+                if (j >= sched.end) break;
+                const u32 seg_end = ci < sched.n_ck ? sched.ck_time[ci] : sched.end;
+                const u32 j0_ = j;
+                if (armed == 0u) BSI_SEGMENT(BSI_CMP0)
+                else if (armed == 1u) BSI_SEGMENT(BSI_CMP1)
+                else if (armed == 2u) BSI_SEGMENT(BSI_CMP2)
+                else BSI_SEGMENT(BSI_CMP3)
+            }
+#undef BSI_SEGMENT
+#undef BSI_CMP0
+#undef BSI_CMP1
+#undef BSI_CMP2
+#undef BSI_CMP3
+#undef BSI_FULL
+        }
+
+        // ---- results: matched lanes -> found queue, others -> retry queue / "no attractor" ----
+        const u32 n_f = __popc(F);
+        const u32 U = valid & ~F;
+        const u32 n_u = __popc(U);
+        u64 base_f = bsi_reserve(&ctr->n_found, n_f);
+        if (n_f) {
+            u32 m = F;
+            while (m) {
+                u32 l = __ffs(m) - 1;
+                m &= m - 1;
+                BsiFound r;
+                r.idx = DENSE ? (((word0 + w) << 5) + l) : in_queue[(w << 5) + l];
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) {
+                    r.y[i] = y_s[(i * 32 + l) * BSI_BLOCK + tid];
+                    r.key[i] = r.y[i];
+                }
+                r.lam = lam_s[l * BSI_BLOCK + tid];
+                r.c = c_s[l * BSI_BLOCK + tid];
+                found_q[base_f++] = r;
+            }
+        }
+        if (final_round) {
+            n_without += n_u;
+            ref_steps += (u64)n_u * stop_t;      // model.py:201: the loop ran out at t = max_t
+        } else {
+            u64 base_u = bsi_reserve(&ctr->n_retry, n_u);
+            u32 m = U;
+            while (m) {
+                u32 l = __ffs(m) - 1;
+                m &= m - 1;
+                retry_q[base_u++] = DENSE ? (((word0 + w) << 5) + l) : in_queue[(w << 5) + l];
+            }
+        }
+    }
+    if (dev_steps) atomicAdd(&ctr->device_steps, dev_steps);
+    if (n_without) atomicAdd(&ctr->n_without, n_without);
+    if (ref_steps) atomicAdd(&ctr->steps, ref_steps);
+}
+
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
+bsi_attract_dense(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end, const BsiSched sched,
+                  int final_round, u64 stop_t, BsiFound *found_q, u64 *retry_q, u32 *scratch,
+                  BsiCounters *ctr) {
+    bsi_main_body<true>(word0, n_words, idx_begin, idx_end, nullptr, 0, sched, final_round, stop_t,
+                        found_q, retry_q, scratch, ctr);
+}
+
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
+bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final_round, u64 stop_t,
+                  BsiFound *found_q, u64 *retry_q, u32 *scratch, BsiCounters *ctr) {
+    bsi_main_body<false>(0, (n_in + 31) >> 5, 0, 0, in_queue, n_in, sched, final_round, stop_t,
+                         found_q, retry_q, scratch, ctr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// attract: exact resolution of the matched lanes
+// ---------------------------------------------------------------------------------------------
+
+// Canonical key = lexicographic minimum over the cycle with node N-1 most significant, i.e. the
+// minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
+// the cycle of found_q[32w + l] from y; walking more than lambda steps only revisits cycle
+// states, so all lanes of a word share the step count max lambda - 1.  lambda == 1: key = y.
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word2);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        if (w >= n_words) continue;
+        BSI_FOR_NODES(BSI_DECL_A)
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_FOR_NODES(BSI_DECL_C)
+        BSI_FOR_NODES(BSI_ZERO_A)
+        u32 valid = 0u, lam_max = 0u;
+        for (u32 l = 0; l < 32; ++l) {
+            u64 q = (w << 5) + l;
+            if (q < n_found) {
+                u64 c_[BSI_KW];
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].y[i];
+                BSI_INSERT(a, l, c_)
+                valid |= 1u << l;
+                lam_max = max(lam_max, found_q[q].lam);
+            }
+        }
+        if (lam_max <= 1u) continue;
+        BSI_FOR_NODES(BSI_COPY_CA)
+        // lt_: lanes where X < c (decided at the most significant differing node)
+#define BSI_LEX_NODE(i)                                                           \
+    lt_ |= bsi_lop3<0x08>(X_(i), c##i, eq_);                                      \
+    eq_ = bsi_lop3<0x90>(eq_, X_(i), c##i);
+#define BSI_SEL_NODE(i) c##i = bsi_lop3<0xCA>(lt_, X_(i), c##i);
+        // 0x08: ~x & c & eq;  0x90: eq & ~(x ^ c);  0xCA: lt ? x : c
+#define BSI_LEX_STEP                                                              \
+    {                                                                             \
+        u32 lt_ = 0u, eq_ = valid;                                                \
+        BSI_LEX_CHUNKS                                                            \
+        if (lt_) { BSI_FOR_NODES(BSI_SEL_NODE) }                                  \
+    }
+        for (u32 k = 1; k < lam_max; k += 2) {
+            BSI_UPDATE(b, a)
+#define X_(i) b##i
+            BSI_LEX_STEP
+#undef X_
+            BSI_UPDATE(a, b)
+#define X_(i) a##i
+            BSI_LEX_STEP
+#undef X_
+        }
+#undef BSI_LEX_STEP
+#undef BSI_SEL_NODE
+#undef BSI_LEX_NODE
+        for (u32 l = 0; l < 32; ++l) {
+            if ((valid >> l) & 1u) {
+                u64 c_[BSI_KW];
+                BSI_EXTRACT(c, l, c_)
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) found_q[(w << 5) + l].key[i] = c_[i];
+            }
+        }
+    }
+}
+
+// Exact mu, then acceptance and aggregation.  With y = x_c on the cycle, let P be the periodic
+// extension of the cycle to all times: P(j) = x_j exactly for j >= mu, so
+//     mu = first j with x_j == P(j),   P(0) = y advanced by (lambda - c mod lambda) mod lambda.
+// a* walks x_j from the problem index, b* walks P(j); three register sets rotate so that no step
+// needs a copy.  Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_attractor_l,
+               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+    __shared__ u32 aux_s[32 * BSI_BLOCK];
+    const u32 tid = threadIdx.x;
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    u64 steps = 0, n_acc = 0, n_rej = 0;
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word3);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        if (w >= n_words) continue;
+        BSI_FOR_NODES(BSI_DECL_A)
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_FOR_NODES(BSI_DECL_C)
+        BSI_FOR_NODES(BSI_ZERO_B)
+        u32 valid = 0u, adv_max = 0u, c_max = 0u;
+        for (u32 l = 0; l < 32; ++l) {
+            u64 q = (w << 5) + l;
+            if (q < n_found) {
+                u64 c_[BSI_KW];
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].y[i];
+                BSI_INSERT(b, l, c_)
+                valid |= 1u << l;
+                const u32 lam = found_q[q].lam, c = found_q[q].c;
+                const u32 adv = (lam - c % lam) % lam;
+                aux_s[l * BSI_BLOCK + tid] = adv;
+                adv_max = max(adv_max, adv);
+                c_max = max(c_max, c);
+            }
+        }
+        // ---- b <- P(0): advance each lane by its own number of steps --------------------------
+#define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
+        {
+            u32 go_ = 0u, next_ev = 0u;
+            for (u32 k = 0; k < adv_max; ++k) {
+                if (k == next_ev) {
+                    go_ = 0u;
+                    next_ev = 0xFFFFFFFFu;
+                    for (u32 l = 0; l < 32; ++l) {
+                        if (!((valid >> l) & 1u)) continue;
+                        u32 adv = aux_s[l * BSI_BLOCK + tid];
+                        if (adv > k) { go_ |= 1u << l; next_ev = min(next_ev, adv); }
+                    }
+                }
+                BSI_UPDATE(c, b)
+                BSI_FOR_NODES(BSI_HOLD_NODE)
+            }
+        }
+#undef BSI_HOLD_NODE
+        // ---- a <- x_lp from the problem index ---------------------------------------------------
+        {
+            // the prefix macro works on (a, b): park P(0) in c meanwhile
+#define BSI_COPY_CB(i) c##i = b##i;
+#define BSI_COPY_BC(i) b##i = c##i;
+            BSI_FOR_NODES(BSI_COPY_CB)
+            BSI_FOR_NODES(BSI_ZERO_A)
+            for (u32 l = 0; l < 32; ++l) {
+                u64 q = (w << 5) + l;
+                if (q < n_found) {
+                    u64 c_[BSI_KW];
+                    u64 lp_lane_ = 0;
+                    BSI_LANE_SETUP(l, found_q[q].idx, c_)
+                    (void)lp_lane_;
+                    BSI_INSERT(a, l, c_)
+                }
+            }
+            BSI_PREFIX(BSI_LP_ORIGIN)
+            BSI_FOR_NODES(BSI_COPY_BC)
+#undef BSI_COPY_CB
+#undef BSI_COPY_BC
+        }
+        // ---- lock-step: mu = first j with x_j == P(j) -------------------------------------------
+        u32 alive = valid;
+#define BSI_LOCK(A, B, Tn, J)                                                     \
+    {                                                                             \
+        u32 p_ = ~alive, q_ = 0u;                                                 \
+        BSI_CMP_FILTER(p_, q_, A, B)                                              \
+        p_ |= q_;                                                                 \
+        if (p_ != 0xFFFFFFFFu) {                                                  \
+            BSI_CMP_REST(p_, A, B)                                                \
+            u32 m_ = ~p_;                                                         \
+            alive &= ~m_;                                                         \
+            while (m_) {                                                          \
+                u32 l_ = __ffs(m_) - 1;                                           \
+                m_ &= m_ - 1;                                                     \
+                aux_s[l_ * BSI_BLOCK + tid] = (J);                                \
+            }                                                                     \
+        }                                                                         \
+        if (alive) { BSI_UPDATE(Tn, A) BSI_UPDATE(A, B) }                         \
+    }
+        {
+            u32 j = 0;
+            while (alive && j <= c_max) {
+                BSI_LOCK(a, b, c, j)
+                if (!alive || j + 1 > c_max) break;
+                BSI_LOCK(c, a, b, j + 1)
+                if (!alive || j + 2 > c_max) break;
+                BSI_LOCK(b, c, a, j + 2)
+                j += 3;
+            }
+        }
+#undef BSI_LOCK
+        if (alive) atomicExch(&ctr->internal_error, 1ull);
+
+        // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
+        u32 todo = valid & ~alive;
+        while (todo) {
+            const u32 l0 = __ffs(todo) - 1;
+            const BsiFound r0 = found_q[(w << 5) + l0];
+            u64 n = 0, s1 = 0, s2 = 0;
+            u32 rest = todo;
+            while (rest) {
+                const u32 l = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const BsiFound *r = found_q + ((w << 5) + l);
+                bool same = true;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) same = same && (r->key[i] == r0.key[i]);
+                if (!same) continue;
+                todo &= ~(1u << l);
+                const u64 mu = aux_s[l * BSI_BLOCK + tid];
+                const u64 lam = r->lam;
+                if (mu + lam <= T) {                     // the loop stops at t = mu + lambda (model.py:201)
+                    steps += BSI_LP_ORIGIN + mu + lam;
+                    if (lam <= max_attractor_l) {        // attract.py:294
+                        const u64 tl = BSI_LP_ORIGIN + mu;   // trajectory_l, attract.py:298
+                        n += 1; s1 += tl; s2 += tl * tl;
+                    } else {
+                        ++n_rej;
+                    }
+                } else {                                 // closes only after max_t
+                    steps += stop_t_cap;
+                    ++n_rej;
+                }
+            }
+            if (n) {
+                bsi_table_add(table, log2_slots, r0.key, n, s1, s2, r0.lam, ctr);
+                n_acc += n;
+            }
+        }
+    }
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
+    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
+}
+
+// ---- attractor table: export / merge ------------------------------------------------------------
+extern "C" __global__ void bsi_table_export(const BsiSlot *table, u32 log2_slots, BsiRec *out,
+                                            u64 cap, u64 *count) {
+    const u64 n_slots = (u64)1 << log2_slots;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots;
+         i += (u64)gridDim.x * blockDim.x) {
+        if (table[i].flag == 2u) {
+            u64 pos = atomicAdd(count, 1ull);
+            if (pos < cap) {
+                BsiRec r;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r.key[k] = 0ull;
+#pragma unroll
+                for (int k = 0; k < BSI_KW; ++k) r.key[k] = table[i].key[k];
+                r.n = table[i].n; r.s1 = table[i].s1; r.s2 = table[i].s2; r.lam = table[i].lam;
+                out[pos] = r;
+            }
+        }
+    }
+}
+
+extern "C" __global__ void bsi_table_merge(BsiSlot *table, u32 log2_slots, const BsiRec *recs, u64 n,
+                                           BsiCounters *ctr) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (u64)gridDim.x * blockDim.x) {
+        if (recs[i].n == 0ull) continue;
+        u64 key[BSI_KW];
+#pragma unroll
+        for (int k = 0; k < BSI_KW; ++k) key[k] = recs[i].key[k];
+        bsi_table_add(table, log2_slots, key, recs[i].n, recs[i].s1, recs[i].s2, (u32)recs[i].lam, ctr);
+    }
+}
+
+#endif  // BSI_MODE == 1
+
+// ---------------------------------------------------------------------------------------------
+// simulate / target / orbits: explicit trajectories
+// ---------------------------------------------------------------------------------------------
+
+// Lane l of thread w simulates problem  indices ? indices[32w + l] : idx_begin + 32w + l  for
+// n_steps steps (reference simulate.py:97-131 == plain iteration with masks) and stores every
+// state as KW code words: out[(q * (n_steps + 1) + t) * KW].
+// With codes != 0 the lanes start from explicit state codes instead (orbit regeneration,
+// reference attract.py:22-25): no prefix, no perturbations, origin fixed nodes only.
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lanes, u64 n_steps,
+                 u64 *out) {
+    const u64 w = (u64)blockIdx.x * BSI_BLOCK + threadIdx.x;
+    if ((w << 5) >= n_lanes) return;
+    BSI_FOR_NODES(BSI_DECL_A)
+    BSI_FOR_NODES(BSI_DECL_B)
+    BSI_FOR_NODES(BSI_ZERO_A)
+    BSI_FOR_FIXVAR(BSI_DECL_FIXVAR)
+    BSI_FOR_PVAR(BSI_DECL_PVAR)
+    u32 valid = 0u;
+    for (u32 l = 0; l < 32; ++l) {
+        u64 q = (w << 5) + l;
+        if (q < n_lanes) {
+            u64 c_[BSI_KW];
+            u64 lp_lane_ = 0;
+            // (the setup also fills the per-lane fixed-node masks; with explicit codes the index
+            //  is irrelevant for them because orbits are only asked for in attract mode)
+            BSI_LANE_SETUP(l, (indices ? indices[q] : idx_begin + q), c_)
+            (void)lp_lane_;
+            if (codes) {
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) c_[i] = codes[q * BSI_KW + i];
+            }
+            BSI_INSERT(a, l, c_)
+            valid |= 1u << l;
+        }
+    }
+    const bool perturbing = codes == nullptr;
+#define BSI_STORE(X, T)                                                           \
+    for (u32 l = 0; l < 32; ++l) {                                                \
+        if ((valid >> l) & 1u) {                                                  \
+            u64 c_[BSI_KW];                                                       \
+            BSI_EXTRACT(X, l, c_)                                                 \
+            u64 *dst = out + (((w << 5) + l) * (n_steps + 1) + (T)) * BSI_KW;     \
+            for (int i = 0; i < BSI_KW; ++i) dst[i] = c_[i];                      \
+        }                                                                         \
+    }
+    BSI_STORE(a, 0)
+    for (u64 t = 1; t <= n_steps; ++t) {
+        BSI_UPDATE(b, a)
+        if (perturbing) { BSI_PERTURB(b, t) }
+        BSI_FOR_NODES(BSI_COPY_AB)
+        BSI_STORE(a, t)
+    }
+#undef BSI_STORE
+}
+
+#if BSI_MODE == 2
+// target (reference target.py:109-133 over model.py:152-236): first time t in [lp, T] at which
+// the constrained nodes equal the target; lp = the lane's own last perturbation time.
+//
+// One round with horizon T (absolute time): lanes that hit report (idx, t_hit).  When `check_closure`
+// is set (max_t beyond this horizon), lanes without a hit are tested for cycle closure --
+// x_T among x_lp .. x_{T-1} -- because after closure no new state, hence no hit, can appear
+// (model.py:201: the reference stops there); lanes neither hit nor closed go to the retry queue.
+// Lanes that end without a hit add their reference stop time to ctr->steps only in the final
+// round (stop time = max_t); closed lanes are reported in closed_q for exact stop-time accounting.
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int check_closure,
+                u64 *hit_idx, u64 *hit_t, u64 hit_cap, u64 *retry_q, u64 *closed_q,
+                BsiCounters *ctr) {
+    __shared__ u32 th_s[32 * BSI_BLOCK];
+    __shared__ u32 lp_s[32 * BSI_BLOCK];
+    const u64 w = (u64)blockIdx.x * BSI_BLOCK + threadIdx.x;
+    if ((w << 5) >= n_lanes) return;
+    BSI_FOR_NODES(BSI_DECL_A)
+    BSI_FOR_NODES(BSI_DECL_B)
+    BSI_FOR_NODES(BSI_DECL_C)
+    BSI_FOR_FIXVAR(BSI_DECL_FIXVAR)
+    BSI_FOR_PVAR(BSI_DECL_PVAR)
+    u32 valid = 0u, hit = 0u, closed = 0u;
+    u64 dev_steps = 0;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: hits and c = x_T;  pass 1 (only if needed): closure test against c
+        BSI_FOR_NODES(BSI_ZERO_A)
+        valid = 0u;
+        for (u32 l = 0; l < 32; ++l) {
+            u64 q = (w << 5) + l;
+            if (q < n_lanes) {
+                u64 c_[BSI_KW];
+                u64 lp_lane_ = BSI_LP_ORIGIN;
+                // (re-running the setup in pass 1 is harmless: it only ORs the same mask bits)
+                BSI_LANE_SETUP(l, (in_queue ? in_queue[q] : idx_begin + q), c_)
+                lp_s[l * BSI_BLOCK + threadIdx.x] = (u32)lp_lane_;
+                BSI_INSERT(a, l, c_)
+                valid |= 1u << l;
+            }
+        }
+        u32 started = 0u;
+        u32 alive = valid & ~hit;
+        for (u64 t = 0;; ++t) {
+            // lanes whose perturbations are all carried out by time t
+            if (t <= BSI_LP_MAX) {
+                for (u32 l = 0; l < 32; ++l)
+                    if (((valid >> l) & 1u) && lp_s[l * BSI_BLOCK + threadIdx.x] == (u32)t) started |= 1u << l;
+            }
+            if (pass == 0) {
+                u32 acc = ~(alive & started);
+                BSI_CMP_TARGET(acc, a)
+                u32 m_ = ~acc;
+                if (m_) {
+                    hit |= m_;
+                    alive &= ~m_;
+                    while (m_) {
+                        u32 l_ = __ffs(m_) - 1;
+                        m_ &= m_ - 1;
+                        th_s[l_ * BSI_BLOCK + threadIdx.x] = (u32)t;
+                    }
+                }
+                if (t >= T || (!alive && t >= BSI_LP_MAX)) break;
+            } else {
+                if (t >= T) break;
+                u32 p_ = ~(alive & started), q_ = 0u;
+                BSI_CMP_FILTER(p_, q_, a, c)
+                p_ |= q_;
+                if (p_ != 0xFFFFFFFFu) {
+                    BSI_CMP_REST(p_, a, c)
+                    u32 m_ = ~p_;
+                    closed |= m_;
+                    alive &= ~m_;
+                }
+                if (!alive) break;
+            }
+            BSI_UPDATE(b, a)
+            BSI_PERTURB(b, (t + 1))
+            BSI_FOR_NODES(BSI_COPY_AB)
+            ++dev_steps;
+        }
+        if (pass == 0) {
+            if (!check_closure || !alive) break;
+            BSI_FOR_NODES(BSI_COPY_CA)
+        }
+    }
+
+    u64 steps = 0;
+    for (u32 l = 0; l < 32; ++l) {
+        if (!((valid >> l) & 1u)) continue;
+        u64 q = (w << 5) + l;
+        u64 idx = in_queue ? in_queue[q] : idx_begin + q;
+        if ((hit >> l) & 1u) {
+            u64 pos = atomicAdd(&ctr->n_hits, 1ull);
+            if (pos < hit_cap) {
+                hit_idx[pos] = idx;
+                hit_t[pos] = th_s[l * BSI_BLOCK + threadIdx.x];
+            }
+            steps += th_s[l * BSI_BLOCK + threadIdx.x];
+        } else if (check_closure && ((closed >> l) & 1u)) {
+            closed_q[atomicAdd(&ctr->n_found, 1ull)] = idx;
+        } else if (check_closure) {
+            retry_q[atomicAdd(&ctr->n_retry, 1ull)] = idx;
+        } else {
+            atomicAdd(&ctr->n_without, 1ull);
+            steps += T > lp_s[l * BSI_BLOCK + threadIdx.x] ? T : lp_s[l * BSI_BLOCK + threadIdx.x];
+        }
+    }
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (dev_steps) atomicAdd(&ctr->device_steps, dev_steps);
+}
+#endif  // BSI_MODE == 2

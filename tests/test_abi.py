@@ -1,0 +1,74 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/bsi.h declares,
+specialises kernels without a GPU, and refuses to run without one (no CPU fallback)."""
+import ctypes
+import os
+import re
+from math import inf
+
+import pytest
+
+from boolsi_b200 import _lib, synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    import __graft_entry__ as g
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    return _lib.lib()
+
+
+def test_exports_match_header(built):
+    header = open(os.path.join(REPO, 'include', 'bsi.h')).read()
+    declared = set(re.findall(r'^(?:int|void|const char \*)\s*\*?(bsi_[a-z0-9_]+)\(', header, re.M))
+    assert declared == set(_lib.EXPORTS)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), name
+    assert built.bsi_abi_version() == 1
+
+
+def _pk(n, k, seed, n_free):
+    cfg = synth.random_attract_problem(n, k, seed, n_free=n_free)
+    return _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                              cfg['origin simulation problem'], cfg['simulation problem variations'])
+
+
+def test_offline_specialisation_and_op_counts(built):
+    pk = _pk(64, 3, 0, 26)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True) as plan:
+        assert plan.n_problems == 2 ** 26
+        ops = plan.op_counts()
+        assert ops['compare_lop3'] == 64 and 0 < ops['update_lop3'] <= 64
+        assert 'lop3.b32' in plan.source()
+        assert len(plan.cubin()) > 10000
+        with pytest.raises(_lib.BsiError) as e:
+            plan.attract_run(0, 32, 10, inf)
+        assert e.value.status == -2          # BSI_E_CUDA: no device, no fallback
+
+
+def test_wide_rules_specialise(built):
+    pk = _pk(24, 6, 1, 8)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True) as plan:
+        assert plan.op_counts()['update_lop3'] > 24
+
+
+def test_bad_arguments(built):
+    pk = _pk(8, 2, 0, 4)
+    with pytest.raises(_lib.BsiError) as e:
+        _lib.Plan(pk, 7, offline=True)
+    assert e.value.status == -1
+    with pytest.raises(_lib.BsiError):
+        _lib.Plan(pk, _lib.MODE_TARGET, offline=True)      # target mode without a target
+
+
+def test_no_gpu_is_an_error_not_a_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    pk = _pk(8, 2, 0, 4)
+    with pytest.raises(_lib.BsiError) as e:
+        _lib.Plan(pk, _lib.MODE_ATTRACT, device=0)
+    assert e.value.status == -2

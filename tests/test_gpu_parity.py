@@ -1,0 +1,179 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes), against the reference-generated
+golden fixtures and against the C oracle on seeded inputs.  Bit-exact: integers only."""
+from math import inf
+
+import numpy as np
+import pytest
+
+import goldenlib
+from boolsi_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _packed(a):
+    return _lib.PackedProblem(a['preds'], a['tts'], a['origin'], a['variations'])
+
+
+def _table_rows(plan):
+    recs = plan.table_read()
+    rows = [(_lib.code_from_words(r['key'][:plan.kw]), int(r['n']), int(r['sum_l']), int(r['sum_l2']),
+             int(r['lam'])) for r in recs]
+    return sorted(rows, key=lambda r: (-r[1], r[0]))     # attract.py:170-186 order
+
+
+@pytest.mark.parametrize('case', goldenlib.cases('attract'), ids=lambda c: c['name'])
+def test_attract_golden(case):
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    assert pk.n_problems == case['n_problems']
+    with _lib.Plan(pk, _lib.MODE_ATTRACT) as plan:
+        st = plan.attract_run(0, pk.n_problems, a['max_t'], a['max_attractor_l'])
+        want = goldenlib.expected_attractor_rows(case)
+        got = _table_rows(plan)
+        assert [(k, n, s1, s2, lam) for k, n, s1, s2, lam in got] == \
+            [(k, n, s1, s2, len(cyc)) for k, n, s1, s2, cyc in want]
+        exp = case['expected']
+        assert st['steps'] == exp['steps']
+        assert st['n_found'] == sum(r[1] for r in want)
+        assert st['n_without'] == sum(1 for r in exp['records'] if r is None)
+        for k, n, s1, s2, cyc in want[:8]:
+            assert plan.attractor_states(k, len(cyc)) == cyc
+
+
+@pytest.mark.parametrize('first_horizon', [1, 2, 5, 64])
+@pytest.mark.parametrize('name', ['attract_rnd64k2s0_f10_t5000_ainf', 'attract_rnd20k2s3_f12_tinf_ainf',
+                                  'attract_cambium2_rand11', 'attract_rulesA_fixed_perturbed',
+                                  'attract_rnd33k3s2_f10_t400_ainf'])
+def test_attract_horizon_rounds(name, first_horizon):
+    """The result may not depend on the detection-round schedule (retry queue path)."""
+    case = [c for c in goldenlib.cases('attract') if c['name'] == name][0]
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, first_horizon=first_horizon, filter_nodes=3) as plan:
+        st = plan.attract_run(0, pk.n_problems, a['max_t'], a['max_attractor_l'])
+        want = goldenlib.expected_attractor_rows(case)
+        assert _table_rows(plan) == [(k, n, s1, s2, len(cyc)) for k, n, s1, s2, cyc in want]
+        assert st['steps'] == case['expected']['steps']
+
+
+def test_attract_ranges_accumulate_and_clear():
+    case = [c for c in goldenlib.cases('attract') if c['name'] == 'attract_cambium2_first12'][0]
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    want = [(k, n, s1, s2, len(cyc)) for k, n, s1, s2, cyc in goldenlib.expected_attractor_rows(case)]
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, chunk_log2=9) as plan:
+        steps = 0
+        for b, e in [(0, 7), (7, 1000), (1000, 1000), (1000, 4001), (4001, 4096)]:   # ragged, empty
+            steps += plan.attract_run(b, e, a['max_t'], a['max_attractor_l'])['steps']
+        assert _table_rows(plan) == want
+        assert steps == case['expected']['steps']
+        plan.table_clear()
+        assert plan.table_count() == 0
+        plan.attract_run(0, 4096, a['max_t'], a['max_attractor_l'])
+        assert _table_rows(plan) == want
+
+
+@pytest.mark.parametrize('case', goldenlib.cases('simulate'), ids=lambda c: c['name'])
+def test_simulate_golden(case):
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    want = goldenlib.expected_simulations(case)
+    with _lib.Plan(pk, _lib.MODE_SIMULATE) as plan:
+        states, st = plan.simulate_run(0, pk.n_problems, a['max_t'])
+        assert len(want) == pk.n_problems
+        for index, codes, _, _ in want:
+            assert [_lib.code_from_words(w) for w in states[index]] == codes
+        # explicit index lists give the same trajectories
+        pick = [w[0] for w in want[::max(1, len(want) // 7)]]
+        sub, _ = plan.simulate_list(pick, a['max_t'])
+        for row, index in zip(sub, pick):
+            assert [_lib.code_from_words(w) for w in row] == want[index][1]
+
+
+@pytest.mark.parametrize('case', goldenlib.cases('target'), ids=lambda c: c['name'])
+def test_target_golden(case):
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    want = goldenlib.expected_simulations(case)
+    tgt = _lib.make_target(a['target_nodes'], a['target_code'], pk.kw)
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt) as plan:
+        hit_index, hit_t, st = plan.target_run(0, pk.n_problems, a['max_t'], a['n_to_find'])
+        assert st['n_found'] == case['expected']['n_hits_total']
+        assert [int(i) for i in hit_index] == [w[0] for w in want]
+        assert [int(t) for t in hit_t] == [len(w[1]) - 1 for w in want]
+        # the reported trajectory of a hit = plain iteration up to the hit time (target.py:129-131)
+        for (index, codes, _, _), t in list(zip(want, hit_t))[:16]:
+            sub, _ = plan.simulate_list([index], int(t))
+            assert [_lib.code_from_words(w) for w in sub[0]] == codes
+
+
+# ---- against the C oracle on seeded inputs larger than the fixtures -------------------------------
+
+def _oracle_table(cfg, max_t, max_a, idx_begin, idx_end):
+    from oracle import coracle
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    rec = coracle.attract_records(sp, max_t, max_a, idx_begin, idx_end)
+    table = coracle.attract_table(rec, sp.kw)
+    rows = sorted(((k, v[0], v[1], v[2], v[3]) for k, v in table.items()), key=lambda r: (-r[1], r[0]))
+    return rows, rec['steps'], int((rec['found'] == 0).sum())
+
+
+@pytest.mark.parametrize('n_nodes,k,seed,n_free,max_t,max_a,lo,hi', [
+    (64, 3, 0, 26, 1000, inf, 0, 1 << 13),              # the headline network, first 8192 problems
+    (64, 3, 1, 26, 1000, inf, (1 << 25) + 5, (1 << 25) + 5 + 3000),   # unaligned range high up
+    (64, 3, 2, 26, 300, 50, 12345, 12345 + 4096),
+    (64, 2, 0, 20, inf, inf, 0, 1 << 14),               # ordered regime, no caps
+    (32, 2, 5, 16, inf, inf, 0, 1 << 16),
+    (48, 3, 7, 14, 4000, inf, 0, 1 << 12),
+    (17, 4, 3, 17, inf, inf, 0, 1 << 15),
+])
+def test_attract_vs_c_oracle(n_nodes, k, seed, n_free, max_t, max_a, lo, hi):
+    cfg = synth.random_attract_problem(n_nodes, k, seed, n_free=n_free)
+    pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                            cfg['origin simulation problem'], cfg['simulation problem variations'])
+    want_rows, want_steps, want_without = _oracle_table(cfg, max_t, max_a, lo, hi)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT) as plan:
+        st = plan.attract_run(lo, hi, max_t, max_a)
+        assert _table_rows(plan) == want_rows
+        assert st['steps'] == want_steps
+        assert st['n_without'] == want_without
+
+
+def test_attract_random_free_subset_vs_c_oracle():
+    rng = np.random.default_rng(11)
+    free = sorted(int(x) for x in rng.choice(64, size=13, replace=False))
+    cfg = synth.random_attract_problem(64, 3, 4, n_free=13, free_nodes=free)
+    pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                            cfg['origin simulation problem'], cfg['simulation problem variations'])
+    want_rows, want_steps, want_without = _oracle_table(cfg, 700, inf, 0, 1 << 13)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT) as plan:
+        st = plan.attract_run(0, 1 << 13, 700, inf)
+        assert _table_rows(plan) == want_rows
+        assert (st['steps'], st['n_without']) == (want_steps, want_without)
+
+
+def test_target_vs_c_oracle_config5_shape():
+    from oracle import coracle
+    cfg = synth.random_target_problem(128, 4, 0, n_free=14, n_target_nodes=5)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    sp = coracle.Space(*args)
+    rec = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 500)
+    want = np.nonzero(rec['reached'])[0]
+    pk = _lib.PackedProblem(*args)
+    tgt = _lib.make_target(cfg['target node set'], cfg['target substate code'], pk.kw)
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt) as plan:
+        hit_index, hit_t, st = plan.target_run(0, pk.n_problems, 500)
+        assert [int(i) for i in hit_index] == [int(i) for i in want]
+        assert [int(t) for t in hit_t] == [int(rec['stop_t'][i]) for i in want]
+
+
+def test_no_device_plan_cannot_run():
+    cfg = synth.random_attract_problem(8, 2, 0, n_free=4)
+    pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                            cfg['origin simulation problem'], cfg['simulation problem variations'])
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True) as plan:
+        with pytest.raises(_lib.BsiError):
+            plan.attract_run(0, 16, 10, inf)
