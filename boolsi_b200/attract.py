@@ -1,0 +1,156 @@
+"""`attract` mode on the GPU path: the drop-in for reference `attract_master` (attract.py:67-230).
+
+Same arguments in, same `db_conn.root.*` post-conditions out; between them the
+work is done by libbsi (bit-sliced CUDA kernels), sharded over the ranks of a
+`torch.distributed` job when there is one -- the replacement for the MPI task farm (mpi.py) -- with
+the per-GPU attractor tables merged by one NCCL all_gather.
+"""
+import logging
+from fractions import Fraction
+from math import inf
+
+import numpy as np
+
+from . import _lib
+from .db import init_attractor_db_structure
+from .problems import shard_range, state_from_code
+
+
+
+class AggregatedAttractor:
+    """Result record with the attributes the reference's consumers read (attract.py:18-45):
+    `states` (min-code state first, cycle order), `frequency`, `trajectory_l_mean`,
+    `trajectory_l_variation_sum` -- the last two derived from the exact integer triple."""
+
+    def __init__(self, key, states, frequency, sum_l, sum_l2):
+        self.key = key
+        self.states = states
+        self.frequency = frequency
+        self.sum_l, self.sum_l2 = sum_l, sum_l2
+        self.trajectory_l_mean = float(Fraction(sum_l, frequency))
+        self.trajectory_l_variation_sum = float(Fraction(sum_l2) - Fraction(sum_l * sum_l, frequency))
+
+
+class AttractEngine:
+    """One plan on one GPU plus the rank's share of the index space."""
+
+    def __init__(self, predecessor_node_lists, truth_tables, origin_simulation_problem,
+                 simulation_problem_variations, device=0, rank=0, world=1, **plan_opts):
+        self.packed = _lib.PackedProblem(predecessor_node_lists, truth_tables,
+                                         origin_simulation_problem, simulation_problem_variations)
+        self.plan = _lib.Plan(self.packed, _lib.MODE_ATTRACT, device=device, **plan_opts)
+        self.rank, self.world, self.device = rank, world, device
+        self.n_problems = self.packed.n_problems
+        self.lo, self.hi = shard_range(self.n_problems, rank, world)
+        self._gather = None
+        self.totals = None
+        if world > 1:
+            import torch
+            # everything on torch's current stream so that the collective is ordered after the kernels
+            self.plan.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        self.plan.close()
+
+    def run(self, max_t=inf, max_attractor_l=inf):
+        """Clear the table, run this rank's problems, merge all ranks' tables (world > 1).
+        Afterwards every rank holds the complete table on its device.
+        :return: run stats of this rank (`steps` etc.) + job totals in `self.totals`"""
+        self.plan.table_clear()
+        st = self.plan.attract_run(self.lo, self.hi, max_t, max_attractor_l)
+        totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
+        if self.world > 1:
+            totals = self._merge_over_ranks(st)
+        self.totals = totals
+        return st
+
+    def _merge_over_ranks(self, st):
+        from .sharding import exchange_tables
+        if self._gather is None:
+            self._gather = {}
+        everyone, headers = exchange_tables(
+            lambda buf: self.plan.table_export_device(buf.data_ptr(), buf.shape[0]),
+            (st['steps'], st['n_found'], st['n_without']), self.world, 'cuda', buffers=self._gather)
+        self.plan.table_clear()
+        for r in range(self.world):
+            n = int(headers[r, 0])
+            if n:
+                self.plan.table_merge_device(everyone[r, 1:].data_ptr(), n)
+        return {'steps': int(headers[:, 1].sum()), 'n_found': int(headers[:, 2].sum()),
+                'n_without': int(headers[:, 3].sum())}
+
+    def attractors(self):
+        """-> list of AggregatedAttractor in the reference's output order (attract.py:170-186:
+        frequency descending, then key ascending), states regenerated as the orbit of the key."""
+        n_nodes = self.packed.n_nodes
+        rows = []
+        for r in self.plan.table_read():
+            rows.append((_lib.code_from_words(r['key'][:self.plan.kw]), int(r['n']), int(r['sum_l']),
+                         int(r['sum_l2']), int(r['lam'])))
+        rows.sort(key=lambda x: (-x[1], x[0]))
+        out = []
+        for key, n, s1, s2, lam in rows:
+            codes = self.plan.attractor_states(key, lam)
+            out.append(AggregatedAttractor(key, [state_from_code(c, n_nodes) for c in codes], n, s1, s2))
+        return out
+
+
+def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                    simulation_problem_variations, max_t=inf, max_attractor_l=inf, device=0, rank=0,
+                    world=1, **plan_opts):
+    """Host structures in, host results out: the whole `attract` job on this rank's GPU (and its
+    peers when `world > 1`).  :return: dict with the sorted attractors and the job totals."""
+    eng = AttractEngine(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                        simulation_problem_variations, device=device, rank=rank, world=world,
+                        **plan_opts)
+    try:
+        eng.run(max_t, max_attractor_l)
+        attractors = eng.attractors()
+        h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + len(eng.plan.cubin()) + \
+            8 * eng.plan.kw * len(attractors)
+        d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * len(a.states) for a in attractors) + 128
+        return {'attractors': attractors, 'n_attractors': len(attractors),
+                'n_found': eng.totals['n_found'], 'n_without': eng.totals['n_without'],
+                'steps_total': eng.totals['steps'], 'h2d_bytes': h2d, 'd2h_bytes': d2h}
+    finally:
+        eng.close()
+
+
+def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_simulation_problem,
+                   simulation_problem_variations, predecessor_node_lists, truth_tables, max_t,
+                   max_attractor_l, n_simulation_problems, storing_all_states, db_conn, packing_db,
+                   output_dirpath, device=0):
+    """Drop-in for reference `attract_master` (attract.py:67-230): same positional arguments, same
+    post-conditions on `db_conn.root` (aggregated_attractors keyed `(-frequency, key)`,
+    aggregated_attractor_keys_by_batch_index, the counters), same return value.
+
+    `mpi_comm`, the batch count, `packing_db` and `output_dirpath` are accepted and ignored (no
+    task farm, no DB packing, no progress file).  `storing_all_states` is ignored too: results
+    follow the default detection mode (SURVEY.md section 7.2 documents where `-r` differs).
+    """
+    log = logging.getLogger()
+    log.info('GPU path will be used to find attractors from {} initial conditions...'.format(
+        n_simulation_problems))
+    if not hasattr(db_conn.root, 'aggregated_attractors'):
+        init_attractor_db_structure(db_conn)
+    res = attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                          simulation_problem_variations, max_t, max_attractor_l, device=device)
+    root = db_conn.root
+    keys = []
+    for a in res['attractors']:
+        sort_key = (-a.frequency, a.key)
+        root.aggregated_attractors[sort_key] = a
+        keys.append(sort_key)
+    root.n_aggregated_attractors.set(len(keys))
+    root.total_frequency.set(res['n_found'])
+    root.aggregated_attractor_keys_by_batch_index.clear()
+    if keys:
+        root.aggregated_attractor_keys_by_batch_index[0] = keys
+        root.n_aggregated_attractor_batches.set(1)
+        root.aggregated_attractor_batch_sizes_lcm.set(len(keys))
+    text = ['Found {} attractors.'.format(len(keys))]
+    if res['n_found'] < n_simulation_problems:
+        text.append('No attractor within the given limits from {:.2%} initial conditions.'.format(
+            1 - res['n_found'] / n_simulation_problems))
+    log.info(' '.join(text))
+    return root.n_aggregated_attractors()

@@ -260,6 +260,19 @@ int compile_plan(bsi_plan *p) {
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
 
+    // in-process cache: the same network + space + mode specialises to the same source
+    static std::mutex cache_mu;
+    static std::map<std::string, std::pair<std::vector<char>, std::string>> cache;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        auto it = cache.find(p->source);
+        if (it != cache.end()) {
+            p->cubin = it->second.first;
+            p->log = it->second.second;
+            return BSI_OK;
+        }
+    }
+
     nvrtcProgram prog;
     nvrtcResult r = nvrtcCreateProgram(&prog, p->source.c_str(), "bsi_kernels.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) return fail(BSI_E_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
@@ -283,6 +296,11 @@ int compile_plan(bsi_plan *p) {
     p->cubin.resize(cubin_size);
     nvrtcGetCUBIN(prog, p->cubin.data());
     nvrtcDestroyProgram(&prog);
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (cache.size() >= 64) cache.clear();
+        cache[p->source] = {p->cubin, p->log};
+    }
     return BSI_OK;
 }
 

@@ -106,7 +106,7 @@ class Space:
 
 
 def _cap(x):
-    return ORC_INF if x is inf or x is None else int(x)
+    return ORC_INF if x is None or x == inf else int(x)
 
 
 def codes_from_words(words):

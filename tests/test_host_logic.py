@@ -1,0 +1,108 @@
+"""CPU tests of the host-side logic: problem decoding, sharding, the result store, and the
+world_size-2 table exchange over gloo (the N>1 path without GPUs)."""
+import os
+import sys
+from math import inf
+
+import numpy as np
+import pytest
+
+import goldenlib
+from boolsi_b200 import problems, synth
+from boolsi_b200.db import ResultStore, init_attractor_db_structure, init_simulation_db_structure
+from oracle import coracle, oracle
+
+
+@pytest.mark.parametrize('case', [c for c in goldenlib.cases() if c['n_problems'] <= 1152],
+                         ids=lambda c: c['name'])
+def test_decode_matches_oracle(case):
+    a = goldenlib.case_args(case)
+    n = problems.count_simulation_problems(a['variations'])
+    assert n == case['n_problems']
+    for index in sorted({0, 1, n // 3, n // 2, n - 1}):
+        state, fixed, pert = problems.decode_simulation_problem(index, a['origin'], a['variations'])
+        code, ofixed, opert = oracle.decode_problem(index, a['origin'], a['variations'])
+        assert sum(1 << i for i, b in enumerate(state) if b) == code
+        assert fixed == ofixed and pert == opert
+        assert problems.state_from_code(code, a['n_nodes']) == state
+
+
+@pytest.mark.parametrize('n,world', [(8, 1), (8, 2), (2 ** 26, 8), (1000, 3), (31, 4), (33, 2), (0, 2)])
+def test_shard_range_partitions(n, world):
+    spans = [problems.shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 == b0 and a0 <= a1
+    assert all(lo % 32 == 0 for lo, _ in spans)
+
+
+def test_result_store_surface():
+    db = ResultStore()
+    init_attractor_db_structure(db)
+    init_simulation_db_structure(db)
+    db.root.aggregated_attractors[(-3, 9)] = 'b'
+    db.root.aggregated_attractors[(-7, 2)] = 'a'
+    assert list(db.root.aggregated_attractors.values()) == ['a', 'b']     # BTree order
+    db.root.total_frequency.change(10)
+    db.root.n_aggregated_attractors.set(2)
+    assert db.root.total_frequency() == 10 and db.root.n_aggregated_attractors() == 2
+    db.cacheMinimize()
+
+
+def _records_from_table(table, kw):
+    rec = np.zeros((len(table), 8), np.int64)
+    for i, (key, (n, s1, s2, lam)) in enumerate(sorted(table.items())):
+        for j in range(kw):
+            rec[i, j] = np.array((key >> (64 * j)) & (2 ** 64 - 1), np.uint64).astype(np.int64)
+        rec[i, 4:] = [n, s1, s2, lam]
+    return rec
+
+
+def _gloo_worker(rank, world, port, n_free, capacity, out_dir):
+    import torch
+    import torch.distributed as dist
+    from boolsi_b200.sharding import exchange_tables
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    cfg = synth.random_attract_problem(20, 2, 3, n_free=n_free)
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    lo, hi = problems.shard_range(sp.n_problems, rank, world)
+    rec = coracle.attract_records(sp, inf, inf, lo, hi, n_threads=1)
+    mine = _records_from_table(coracle.attract_table(rec, sp.kw), sp.kw)
+
+    def export(buf):
+        m = min(len(mine), buf.shape[0])
+        buf.zero_()
+        buf[:m].copy_(torch.from_numpy(mine[:m]))
+        return len(mine)
+
+    everyone, headers = exchange_tables(export, (rec['steps'], int(rec['found'].sum()), 0), world, 'cpu',
+                                        capacity=capacity)
+    merged = {}
+    for r in range(world):
+        for row in everyone[r, 1:1 + int(headers[r, 0])].numpy():
+            key = int(np.array(row[0], np.int64).astype(np.uint64))
+            cur = merged.setdefault(key, [0, 0, 0, int(row[7])])
+            cur[0] += int(row[4]); cur[1] += int(row[5]); cur[2] += int(row[6])
+    np.save(os.path.join(out_dir, 'r%d.npy' % rank),
+            np.array([[k] + v for k, v in sorted(merged.items())] + [[-1, int(headers[:, 1].sum()), 0, 0, 0]],
+                     dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('capacity', [4096, 1])     # 1 forces the overflow-and-retry protocol
+def test_two_rank_exchange_over_gloo(tmp_path, capacity):
+    import torch.multiprocessing as mp
+    n_free, world = 10, 2
+    port = 29500 + (os.getpid() + capacity) % 2000
+    mp.spawn(_gloo_worker, args=(world, port, n_free, capacity, str(tmp_path)), nprocs=world, join=True)
+    cfg = synth.random_attract_problem(20, 2, 3, n_free=n_free)
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    rec = coracle.attract_records(sp, inf, inf)
+    want = [[k] + v for k, v in sorted(coracle.attract_table(rec, sp.kw).items())]
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), 'r%d.npy' % r), allow_pickle=True).tolist()
+        assert got[:-1] == want                       # every rank holds the complete, identical table
+        assert got[-1][1] == rec['steps']
