@@ -123,40 +123,54 @@ def run_reference(a):
 
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled through NVML every few ms DURING the timed region
+    (the same quantities as the recipe's nvidia-smi line: clocks.sm, clocks.max.sm,
+    clocks_event_reasons.*)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x4: 'sw_power_cap'}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((mhz, reasons, power))
+            except Exception as e:      # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.004)
 
     def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == 'Active'})
-        # under load = the upper half of the samples (the sampler also sees idle gaps)
-        load = sm[len(sm) // 2:] if sm else []
-        return {'sm_mhz': load[len(load) // 2] if load else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable: %s' % self.err]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(n for b, n in self.REASONS.items() if bits & b),
+                'samples': len(sm), 'power_w_max': max(r[2] for r in self.rows)}
 
 
 # ---- GPU side -------------------------------------------------------------------------------------

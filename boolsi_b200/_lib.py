@@ -30,6 +30,7 @@ EXPORTS = [
     'bsi_attract_table_clear', 'bsi_attract_table_count', 'bsi_attract_table_read',
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
+    'bsi_measure_update_rate',
 ]
 
 
@@ -125,6 +126,7 @@ def lib():
                                      C.POINTER(RunStats)]
         L.bsi_measure_lop3_peak.argtypes = [i, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.POINTER(i)]
+        L.bsi_measure_update_rate.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -295,6 +297,11 @@ class Plan:
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         check(lib().bsi_plan_launch_config(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {'n_sms': a.value, 'block_threads': b.value, 'blocks_per_sm': c.value}
+
+    def measure_update_rate(self):
+        w, l = C.c_double(), C.c_double()
+        check(lib().bsi_measure_update_rate(self._h, C.byref(w), C.byref(l)))
+        return {'word_steps_per_s': w.value, 'lop3_per_s': l.value}
 
     def set_stream(self, cuda_stream):
         check(lib().bsi_plan_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -218,7 +218,7 @@ int launch(bsi_plan *p, CUfunction f, unsigned grid, unsigned block, size_t smem
 // ---- filter-node choice: a small host-side activity probe of the network ---------------------
 // (tuning only: the filter never decides a result, every filter pass is followed by a full
 //  compare.)  Nodes that keep toggling late in random trajectories discriminate states best.
-std::vector<int> choose_filter(const bsi::Model &m, int want) {
+std::vector<int> choose_filter(const bsi::Model &m, int want, std::vector<int> *second, int want2) {
     const int n = m.n;
     want = std::min(want, n);
     std::vector<uint8_t> x(n), y(n);
@@ -247,16 +247,23 @@ std::vector<int> choose_filter(const bsi::Model &m, int want) {
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return toggles[a] > toggles[b]; });
     std::vector<int> f(order.begin(), order.begin() + want);
     std::sort(f.begin(), f.end());
+    if (second) {
+        second->assign(order.begin() + want, order.begin() + std::min(n, want + want2));
+        std::sort(second->begin(), second->end());
+    }
     return f;
 }
 
 int compile_plan(bsi_plan *p) {
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
-    std::vector<int> filter = choose_filter(p->m, f_nodes);
+    std::vector<int> filter2;
+    std::vector<int> filter = choose_filter(p->m, f_nodes, &filter2, 12);
     p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
     if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
-    const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
-    p->source = bsi::generate_header(p->m, filter, p->block, min_blocks, p->info);
+    // register cap of the trajectory kernels: 3 warps per scheduler when the state fits (measured
+    // best for N = 64), otherwise whatever the block size allows
+    const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : (p->m.n <= 64 && p->block == 64 ? 6 : 1);
+    p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, p->info);
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
 
@@ -329,7 +336,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mod, "bsi_resolve_mu"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mod, "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mod, "bsi_table_merge"));
-        p->main_smem = (size_t)32 * p->block * (8 + 8 * p->m.kw);
+        p->main_smem = (size_t)3 * p->info.filter2_nodes * p->block * 4;
         if (p->main_smem > 48 * 1024) {
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
             CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
@@ -545,7 +552,7 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
     const size_t found_bytes = 16 + 16 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    const size_t scratch_bytes = (size_t)main_grid * p->block * 3 * p->m.n * sizeof(uint32_t);
+    const size_t scratch_bytes = (size_t)main_grid * p->block * (3 * p->m.n + 64 + 64 * p->m.kw) * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
@@ -890,6 +897,38 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
     st.launches = p->launches - launches0;
     if (n_hits) *n_hits = written;
     if (stats) *stats = st;
+    return BSI_OK;
+}
+
+// ---- the bare update loop of this plan's network --------------------------------------------------
+int bsi_measure_update_rate(bsi_plan *p, double *word_steps_per_s, double *lop3_per_s) {
+    int rc = need_device(p, -1);
+    if (rc) return rc;
+    CtxGuard g(p);
+    CUfunction f = nullptr;
+    CU_CHECK(cuModuleGetFunction(&f, p->mod, "bsi_update_rate"));
+    if ((rc = ensure(p, p->misc, 256))) return rc;
+    int per_sm = 0;
+    CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, p->block, 0));
+    per_sm = std::max(1, std::min(per_sm, 8));
+    unsigned grid = (unsigned)(p->n_sms * per_sm);
+    uint32_t pairs = 20000, seed = 777;
+    void *args[] = {&pairs, &seed, &p->misc.p};
+    p->events_used = 0;
+    CUevent e0, e1;
+    if ((rc = get_event(p, &e0)) || (rc = get_event(p, &e1))) return rc;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU_CHECK(cuEventRecord(e0, p->stream));
+        if ((rc = launch(p, f, grid, p->block, 0, args))) return rc;
+        CU_CHECK(cuEventRecord(e1, p->stream));
+        CU_CHECK(cuEventSynchronize(e1));
+        double ms = 0;
+        if ((rc = elapsed(e0, e1, &ms))) return rc;
+        if (rep > 0) best = std::max(best, (double)grid * p->block * pairs * 2.0 / (ms * 1e-3));
+    }
+    if (word_steps_per_s) *word_steps_per_s = best;
+    if (lop3_per_s) *lop3_per_s = best * p->info.update_lop3;
     return BSI_OK;
 }
 

@@ -311,6 +311,7 @@ inline std::string load_model(const bsi_network_desc *net, const bsi_space_desc 
 }
 
 struct GenInfo {
+    int filter2_nodes = 0;   // stage-2 filter words per checkpoint slot (shared memory)
     int update_lop3 = 0;     // LOP3 per word-step of the autonomous update
     int compare_lop3 = 0;    // full compare
     int filter_lop3 = 0;     // cheap pre-compare
@@ -326,7 +327,8 @@ inline std::string node_list_macro(const std::string &name, int n) {
 }
 
 // The macro header.  `filter` = nodes of the cheap pre-compare, in order.
-inline std::string generate_header(const Model &m, const std::vector<int> &filter, int block_threads,
+inline std::string generate_header(const Model &m, const std::vector<int> &filter,
+                                   const std::vector<int> &filter2, int block_threads,
                                    int min_blocks, GenInfo &info) {
     std::ostringstream o;
     const int n = m.n;
@@ -361,8 +363,38 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
     // ---- update: D = F(S) with fixed nodes folded in (model.py:16-49) ---------------------
     {
         Lop3Synth syn("S");
-        std::ostringstream stmts;
-        for (int i = 0; i < n; ++i) {
+        // Emission order: greedily pick the node whose evaluation retires the most old-state words
+        // (a source dies once its last reader has been emitted), so that the old and the new
+        // state overlap in as few registers as possible.
+        std::vector<int> order;
+        {
+            std::vector<std::vector<int>> srcs(n);
+            std::vector<int> readers(n, 0);
+            for (int i = 0; i < n; ++i) {
+                bool constant = m.fixed.count(i) && !fixvar_nodes.count(i);
+                if (!constant) {
+                    BoolFn r = m.fn[i].reduced();
+                    std::set<int> uniq(r.vars.begin(), r.vars.end());
+                    srcs[i].assign(uniq.begin(), uniq.end());
+                }
+                for (int v : srcs[i]) ++readers[v];
+            }
+            std::vector<char> done(n, 0);
+            for (int step = 0; step < n; ++step) {
+                int best = -1, best_score = -1000;
+                for (int i = 0; i < n; ++i) {
+                    if (done[i]) continue;
+                    int kills = 0;
+                    for (int v : srcs[i]) if (readers[v] == 1) ++kills;
+                    int score = 4 * kills - (int)srcs[i].size();
+                    if (score > best_score) { best_score = score; best = i; }
+                }
+                done[best] = 1;
+                order.push_back(best);
+                for (int v : srcs[best]) --readers[v];
+            }
+        }
+        for (int i : order) {
             std::string dst = "D##" + std::to_string(i);
             auto fx = m.fixed.find(i);
             bool varfix = fixvar_nodes.count(i) > 0;
@@ -431,6 +463,13 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         for (int i = 0; i < n; ++i)
             if (!in_filter[i])
                 o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", (P)[(unsigned long long)" << i << " * (S)]);";
+        o << " }\n#define BSI_F2 " << std::max<size_t>(1, filter2.size()) << "\n";
+        o << "#define BSI_CMP_FILTER2_MEM(acc, X, P, S) {";
+        for (size_t g = 0; g < filter2.size(); ++g)
+            o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << g << " * (S)]);";
+        o << " }\n#define BSI_STORE_FILTER2(X, P, S) {";
+        for (size_t g = 0; g < filter2.size(); ++g)
+            o << " (P)[" << g << " * (S)] = X##" << filter2[g] << ";";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
         for (int i = 0; i < n; ++i) o << " (P)[(unsigned long long)" << i << " * (S)] = X##" << i << ";";
         o << " }\n#define BSI_DUMP(X, A) {";
@@ -446,6 +485,7 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         for (int q = 0; q < open; ++q) o << " }";
         o << "\n";
         info.filter_lop3 = (int)filter.size();
+        info.filter2_nodes = (int)std::max<size_t>(1, filter2.size());
         info.compare_lop3 = n;
         info.filter_nodes = filter;
     }

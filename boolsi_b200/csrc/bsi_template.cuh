@@ -215,33 +215,40 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // ---------------------------------------------------------------------------------------------
 #if BSI_MODE == 1
 
-// dynamic shared memory of the main kernel: per (lane, thread) detection records
-//   u32 lam[32][BLOCK], u32 c[32][BLOCK], u64 y[KW][32][BLOCK]
+// dynamic shared memory of the main kernel: the stage-2 filter words of the three checkpoint
+// slots, u32 f2[3][BSI_F2][BLOCK].  The per-thread scratch in global memory (L2-resident, sized by
+// the persistent grid) holds, per thread: 3 full checkpoints [3][N], then the detection records
+// of its 32 lanes: u32 lam[32], u32 c[32], u64 y[KW][32].
 extern __shared__ __align__(16) unsigned char bsi_smem[];
 
 // full compare of a state held in local memory with a checkpoint in the scratch: lanes of
 // `cand` whose N words all agree
-__device__ __noinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 sstride, u32 cand) {
+__device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 sstride, u32 cand) {
     u32 acc = ~cand;
+#pragma unroll 1
     for (int i = 0; i < BSI_N && acc != 0xFFFFFFFFu; ++i) acc |= xs[i] ^ ck[(u64)i * sstride];
     return ~acc;
 }
 
 // detection record of the lanes in m: cycle length, checkpoint time and the matched state code
-__device__ __noinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
-                                        u64 *y_s) {
-    const u32 tid = threadIdx.x;
+__device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
+                                           u64 *y_s, u64 sstride) {
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
         u64 code[BSI_KW];
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) code[k] = 0ull;
-        for (int i = 0; i < BSI_N; ++i) code[i >> 6] |= (u64)((xs[i] >> l) & 1u) << (i & 63);
-        lam_s[l * BSI_BLOCK + tid] = lam;
-        c_s[l * BSI_BLOCK + tid] = c;
 #pragma unroll
-        for (int k = 0; k < BSI_KW; ++k) y_s[(k * 32 + l) * BSI_BLOCK + tid] = code[k];
+        for (int k = 0; k < BSI_KW; ++k) {
+#pragma unroll 1
+            for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
+                code[k] |= (u64)((xs[i] >> l) & 1u) << (i & 63);
+        }
+        lam_s[l * sstride] = lam;
+        c_s[l * sstride] = c;
+#pragma unroll
+        for (int k = 0; k < BSI_KW; ++k) y_s[(k * 32 + l) * sstride] = code[k];
     }
 }
 
@@ -253,12 +260,15 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                                               const BsiSched &sched, int final_round, u64 stop_t,
                                               BsiFound *found_q, u64 *retry_q, u32 *scratch,
                                               BsiCounters *ctr) {
-    u32 *lam_s = (u32 *)bsi_smem;
-    u32 *c_s = lam_s + 32 * BSI_BLOCK;
-    u64 *y_s = (u64 *)(c_s + 32 * BSI_BLOCK);
     const u32 tid = threadIdx.x;
+    u32 *const f2_s = (u32 *)bsi_smem + tid;                          // [slot][BSI_F2][BLOCK]
     const u64 sstride = (u64)gridDim.x * BSI_BLOCK;
-    u32 *const my_scratch = scratch + ((u64)blockIdx.x * BSI_BLOCK + tid);
+    const u64 gtid = (u64)blockIdx.x * BSI_BLOCK + tid;
+    u32 *const my_scratch = scratch + gtid;
+    // detection records of this thread's 32 lanes (rarely written): after the 3 checkpoint slots
+    u32 *const lam_s = scratch + 3ull * BSI_N * sstride + gtid;       // [32][sstride]
+    u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride]
+    u64 *const y_s = (u64 *)(scratch + (3ull * BSI_N + 64ull) * sstride) + gtid;   // [KW][32][sstride]
     u64 dev_steps = 0, n_without = 0, ref_steps = 0;
 
     for (;;) {
@@ -299,10 +309,11 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             u32 j = 0, ci = 0, armed = 0;
             u32 st0 = 0, st1 = 0, st2 = 0;       // checkpoint time held by each slot
 
-            // Cold path, taken when some lane passes a filter: the state goes to local memory and
-            // two out-of-line functions do the full compare against the checkpoint scratch and
-            // record the matching lanes, so that the hot loop's register allocation only sees
-            // the state words, the filter words and a handful of scalars.
+            // Cold path, taken when some lane passes a register filter.  Stage 2 refines the
+            // candidate lanes against BSI_F2 more checkpoint words kept in shared memory (inline,
+            // a handful of LDS); only if a lane survives that too is the state dumped to local
+            // memory for the full compare against the scratch (rolled loops: the hot loop's
+            // register allocation only sees the state words, the filter words and a few scalars).
 #define BSI_FULL(XS, J, S, ST, ACC)                                                  \
     {                                                                                \
         u32 cand_ = ~(ACC) & alive;                                                  \
@@ -311,45 +322,76 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
-                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s);               \
+                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s, sstride);      \
             }                                                                        \
         }                                                                            \
     }
-#define BSI_CMP1(X, J)                                                               \
+#define BSI_STAGE2(X, S, ACC)                                                        \
+    if (ACC != 0xFFFFFFFFu) {                                                        \
+        const u32 *p2_ = f2_s + (S) * BSI_F2 * BSI_BLOCK;                             \
+        BSI_CMP_FILTER2_MEM(ACC, X, p2_, BSI_BLOCK)                                  \
+    }
+            // register filters of state X against the armed slots: p_s = lanes that CANNOT match
+#define BSI_FILT0(X) {}
+#define BSI_FILT1(X)                                                                 \
     {                                                                                \
-        u32 p0 = ~alive, q0 = 0u;                                                    \
+        u32 q0 = 0u;                                                                 \
+        p0 = ~alive;                                                                 \
         BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
         p0 |= q0;                                                                    \
-        if (p0 != 0xFFFFFFFFu) {                                                     \
-            u32 xs_[BSI_N];                                                          \
-            BSI_DUMP(X, xs_)                                                         \
-            BSI_FULL(xs_, J, 0, st0, p0)                                             \
-        }                                                                            \
     }
-#define BSI_CMP2(X, J)                                                               \
+#define BSI_FILT2(X)                                                                 \
     {                                                                                \
-        u32 p0 = ~alive, q0 = 0u, p1 = p0, q1 = 0u;                                  \
+        u32 q0 = 0u, q1 = 0u;                                                        \
+        p0 = p1 = ~alive;                                                            \
         BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
         BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
         p0 |= q0;                                                                    \
         p1 |= q1;                                                                    \
-        if ((p0 & p1) != 0xFFFFFFFFu) {                                              \
-            u32 xs_[BSI_N];                                                          \
-            BSI_DUMP(X, xs_)                                                         \
-            BSI_FULL(xs_, J, 0, st0, p0)                                             \
-            BSI_FULL(xs_, J, 1, st1, p1)                                             \
-        }                                                                            \
     }
-#define BSI_CMP3(X, J)                                                               \
+#define BSI_FILT3(X)                                                                 \
     {                                                                                \
-        u32 p0 = ~alive, q0 = 0u, p1 = p0, q1 = 0u, p2 = p0, q2 = 0u;                \
+        u32 q0 = 0u, q1 = 0u, q2 = 0u;                                               \
+        p0 = p1 = p2 = ~alive;                                                       \
         BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
         BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
         BSI_CMP_FILTER(p2, q2, X, k2_)                                               \
         p0 |= q0;                                                                    \
         p1 |= q1;                                                                    \
         p2 |= q2;                                                                    \
-        if (bsi_lop3<0x80>(p0, p1, p2) != 0xFFFFFFFFu) {                             \
+    }
+#define BSI_ANY0 false
+#define BSI_ANY1 (p0 != 0xFFFFFFFFu)
+#define BSI_ANY2 ((p0 & p1) != 0xFFFFFFFFu)
+#define BSI_ANY3 (bsi_lop3<0x80>(p0, p1, p2) != 0xFFFFFFFFu)
+            // slow handlers: stage 2, then the full compare of the surviving candidates
+#define BSI_SLOW0(X, J) {}
+#define BSI_SLOW1(X, J)                                                              \
+    {                                                                                \
+        BSI_STAGE2(X, 0, p0)                                                         \
+        if (BSI_ANY1) {                                                              \
+            u32 xs_[BSI_N];                                                          \
+            BSI_DUMP(X, xs_)                                                         \
+            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+        }                                                                            \
+    }
+#define BSI_SLOW2(X, J)                                                              \
+    {                                                                                \
+        BSI_STAGE2(X, 0, p0)                                                         \
+        BSI_STAGE2(X, 1, p1)                                                         \
+        if (BSI_ANY2) {                                                              \
+            u32 xs_[BSI_N];                                                          \
+            BSI_DUMP(X, xs_)                                                         \
+            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+            BSI_FULL(xs_, J, 1, st1, p1)                                             \
+        }                                                                            \
+    }
+#define BSI_SLOW3(X, J)                                                              \
+    {                                                                                \
+        BSI_STAGE2(X, 0, p0)                                                         \
+        BSI_STAGE2(X, 1, p1)                                                         \
+        BSI_STAGE2(X, 2, p2)                                                         \
+        if (BSI_ANY3) {                                                              \
             u32 xs_[BSI_N];                                                          \
             BSI_DUMP(X, xs_)                                                         \
             BSI_FULL(xs_, J, 0, st0, p0)                                             \
@@ -357,24 +399,40 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             BSI_FULL(xs_, J, 2, st2, p2)                                             \
         }                                                                            \
     }
-#define BSI_CMP0(X, J) {}
-            // n_ steps from time j, comparing every new state with the armed slots
-#define BSI_SEGMENT(CMP)                                                             \
+            // n_ steps from time j, comparing every new state with the armed slots.  The inner
+            // loop is the hot path: two updates, their register filters and ONE taken branch;
+            // a filter pass leaves the loop for the handler below and re-enters afterwards.
+#define BSI_SEGMENT(A)                                                               \
     {                                                                                \
         u32 n_ = seg_end - j;                                                        \
+        u32 p0 = 0xFFFFFFFFu, p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;                    \
         for (; n_ >= 2u && alive; n_ -= 2u, j += 2u) {                               \
             BSI_UPDATE(b, a)                                                         \
-            CMP(b, j + 1u)                                                           \
+            BSI_FILT##A(b)                                                           \
+            if (__builtin_expect(BSI_ANY##A, 0)) goto slow_b##A;                     \
+          back_b##A:                                                                 \
             BSI_UPDATE(a, b)                                                         \
-            CMP(a, j + 2u)                                                           \
+            BSI_FILT##A(a)                                                           \
+            if (__builtin_expect(BSI_ANY##A, 0)) goto slow_a##A;                     \
+          back_a##A:;                                                                \
         }                                                                            \
         if (n_ == 1u && alive) {                                                     \
             BSI_UPDATE(b, a)                                                         \
-            CMP(b, j + 1u)                                                           \
+            BSI_FILT##A(b)                                                           \
+            if (BSI_ANY##A) { BSI_SLOW##A(b, j + 1u) }                               \
             BSI_FOR_NODES(BSI_COPY_AB)                                               \
             j += 1u;                                                                 \
             n_ = 0u;                                                                 \
         }                                                                            \
+        if (false) {                                                                 \
+          slow_b##A:                                                                 \
+            BSI_SLOW##A(b, j + 1u)                                                   \
+            goto back_b##A;                                                          \
+          slow_a##A:                                                                 \
+            BSI_SLOW##A(a, j + 2u)                                                   \
+            goto back_a##A;                                                          \
+        }                                                                            \
+        (void)p0; (void)p1; (void)p2;                                                \
         dev_steps += (seg_end - j0_) - n_;                                           \
     }
             while (alive) {
@@ -383,6 +441,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                     const u32 s = sched.ck_slot[ci];
                     u32 *p_ = my_scratch + (u64)s * BSI_N * sstride;
                     BSI_STORE_ALL(a, p_, sstride)
+                    BSI_STORE_FILTER2(a, (f2_s + s * BSI_F2 * BSI_BLOCK), BSI_BLOCK)
                     if (s == 0u) { BSI_FOR_FILTER(BSI_SAVE_K0) st0 = j; }
                     else if (s == 1u) { BSI_FOR_FILTER(BSI_SAVE_K1) st1 = j; }
                     else { BSI_FOR_FILTER(BSI_SAVE_K2) st2 = j; }
@@ -393,17 +452,14 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 if (j >= sched.end) break;
                 const u32 seg_end = ci < sched.n_ck ? sched.ck_time[ci] : sched.end;
                 const u32 j0_ = j;
-                if (armed == 0u) BSI_SEGMENT(BSI_CMP0)
-                else if (armed == 1u) BSI_SEGMENT(BSI_CMP1)
-                else if (armed == 2u) BSI_SEGMENT(BSI_CMP2)
-                else BSI_SEGMENT(BSI_CMP3)
+                if (armed == 0u) BSI_SEGMENT(0)
+                else if (armed == 1u) BSI_SEGMENT(1)
+                else if (armed == 2u) BSI_SEGMENT(2)
+                else BSI_SEGMENT(3)
             }
 #undef BSI_SEGMENT
-#undef BSI_CMP0
-#undef BSI_CMP1
-#undef BSI_CMP2
-#undef BSI_CMP3
 #undef BSI_FULL
+#undef BSI_STAGE2
         }
 
         // ---- results: matched lanes -> found queue, others -> retry queue / "no attractor" ----
@@ -420,11 +476,11 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 r.idx = DENSE ? (((word0 + w) << 5) + l) : in_queue[(w << 5) + l];
 #pragma unroll
                 for (int i = 0; i < BSI_KW; ++i) {
-                    r.y[i] = y_s[(i * 32 + l) * BSI_BLOCK + tid];
+                    r.y[i] = y_s[(i * 32 + l) * sstride];
                     r.key[i] = r.y[i];
                 }
-                r.lam = lam_s[l * BSI_BLOCK + tid];
-                r.c = c_s[l * BSI_BLOCK + tid];
+                r.lam = lam_s[l * sstride];
+                r.c = c_s[l * sstride];
                 found_q[base_f++] = r;
             }
         }
@@ -718,6 +774,27 @@ extern "C" __global__ void bsi_table_merge(BsiSlot *table, u32 log2_slots, const
 }
 
 #endif  // BSI_MODE == 1
+
+// ---------------------------------------------------------------------------------------------
+// measurement: the bare update loop (no compare, no stores) of THIS network -- the practical
+// ceiling of the trajectory kernels, to set beside the ideal-chain lop3 peak
+// ---------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_update_rate(u32 pairs, u32 seed, u32 *out) {
+    BSI_FOR_NODES(BSI_DECL_A)
+    BSI_FOR_NODES(BSI_DECL_B)
+    BSI_FOR_FIXVAR(BSI_DECL_FIXVAR)
+    u32 x_ = seed ^ (blockIdx.x * BSI_BLOCK + threadIdx.x) * 0x9E3779B9u;
+#define BSI_SEED_A(i) x_ = x_ * 1664525u + 1013904223u; a##i = x_;
+    BSI_FOR_NODES(BSI_SEED_A)
+#undef BSI_SEED_A
+    for (u32 k = 0; k < pairs; ++k) { BSI_UPDATE(b, a) BSI_UPDATE(a, b) }
+    u32 acc = 0u;
+#define BSI_FOLD_A(i) acc ^= a##i;
+    BSI_FOR_NODES(BSI_FOLD_A)
+#undef BSI_FOLD_A
+    if (acc == 0x13572468u) out[0] = acc;
+}
 
 // ---------------------------------------------------------------------------------------------
 // simulate / target / orbits: explicit trajectories

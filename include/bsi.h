@@ -116,7 +116,7 @@ typedef struct bsi_plan_opts {
     uint32_t chunk_log2;       /* problems per launch wave; 0 = auto (26) */
     uint32_t keep_source;      /* unused: the generated source is always kept */
     uint32_t block_threads;    /* threads per block of the trajectory kernels; 0 = auto (64) */
-    uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto (1) */
+    uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto       */
     uint32_t reserved[9];
 } bsi_plan_opts;
 
@@ -224,6 +224,11 @@ int bsi_target_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_
 /* Integer-logic roofline microbenchmark: independent LOP3 chains on every SM of `device`;
  * returns thread-level lop3.b32 results per second and the SM clock (MHz) seen during the run. */
 int bsi_measure_lop3_peak(int device, double *lop3_per_s, double *sm_clock_mhz, int *n_sms);
+
+/* The bare update loop of the plan's own network (no compare, no stores), all SMs busy:
+ * 32-lane word-steps per second and the lop3.b32 rate that implies.  The practical ceiling of the
+ * trajectory kernels (arbitrary three-register operands), to set beside the ideal-chain peak. */
+int bsi_measure_update_rate(bsi_plan *plan, double *word_steps_per_s, double *lop3_per_s);
 
 #ifdef __cplusplus
 }

@@ -10,10 +10,13 @@ n_free = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 cfg = synth.random_attract_problem(64, 3, 0, n_free=n_free)
 pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
                         cfg['origin simulation problem'], cfg['simulation problem variations'])
-for opts in ({}, {'filter_nodes': 8}, {'filter_nodes': 16}):
+import ast
+variants = [ast.literal_eval(v) for v in sys.argv[2:]] or [{}]
+for opts in variants:
     t = time.time()
     plan = _lib.Plan(pk, _lib.MODE_ATTRACT, **opts)
     print('plan', opts, 'create s', round(time.time() - t, 2), plan.launch_config(), plan.op_counts(), flush=True)
+    print('update-only rate', plan.measure_update_rate(), flush=True)
     for rep in range(3):
         plan.table_clear()
         st = plan.attract_run(0, pk.n_problems, 1000)
