@@ -71,11 +71,14 @@ class AttractEngine:
         everyone, headers = exchange_tables(
             lambda buf: self.plan.table_export_device(buf.data_ptr(), buf.shape[0]),
             (st['steps'], st['n_found'], st['n_without']), self.world, 'cuda', buffers=self._gather)
-        self.plan.table_clear()
-        for r in range(self.world):
-            n = int(headers[r, 0])
-            if n:
-                self.plan.table_merge_device(everyone[r, 1:].data_ptr(), n)
+        # fold the OTHER ranks' records into this rank's table (header rows and unused rows have
+        # n == 0 and are skipped by the merge kernel): two launches, no host synchronisation
+        rows = everyone.shape[1]
+        if self.rank > 0:
+            self.plan.table_merge_device(everyone[0].data_ptr(), self.rank * rows)
+        if self.rank < self.world - 1:
+            self.plan.table_merge_device(everyone[self.rank + 1].data_ptr(),
+                                         (self.world - 1 - self.rank) * rows)
         return {'steps': int(headers[:, 1].sum()), 'n_found': int(headers[:, 2].sum()),
                 'n_without': int(headers[:, 3].sum())}
 

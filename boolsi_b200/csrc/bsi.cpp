@@ -550,9 +550,9 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
     const uint32_t chunk_log2 = p->opts.chunk_log2 ? p->opts.chunk_log2 : 26;
     if (chunk_log2 < 5 || chunk_log2 > 34) return fail(BSI_E_ARG, "chunk_log2 out of range");
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
-    const size_t found_bytes = 16 + 16 * (size_t)p->m.kw;
+    const size_t found_bytes = 24 + 24 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    const size_t scratch_bytes = (size_t)main_grid * p->block * (3 * p->m.n + 64 + 64 * p->m.kw) * sizeof(uint32_t);
+    const size_t scratch_bytes = (size_t)main_grid * p->block * (3 * p->m.n + 96 + 128 * p->m.kw) * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
@@ -653,8 +653,9 @@ int bsi_attract_table_clear(bsi_plan *p) {
     int rc = need_device(p, BSI_MODE_ATTRACT);
     if (rc) return rc;
     CtxGuard g(p);
+    // asynchronous on the plan's stream (every later call is ordered after it)
     CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
-    CU_CHECK(cuStreamSynchronize(p->stream));
+    CU_CHECK(cuMemsetD8Async(p->ctr.p + offsetof(Counters, table_full), 0, 8, p->stream));
     return BSI_OK;
 }
 
@@ -665,10 +666,13 @@ static int export_table(bsi_plan *p, CUdeviceptr out, uint64_t cap, uint64_t *n)
     if (out && cap) CU_CHECK(cuMemsetD8Async(out, 0, cap * sizeof(bsi_attractor_rec), p->stream));
     void *args[] = {&p->table.p, &p->table_log2, &out, &cap, &p->misc.p};
     if ((rc = launch(p, p->f_export, (unsigned)(p->n_sms * 4), 256, 0, args))) return rc;
-    uint64_t count = 0;
+    uint64_t count = 0, full = 0;
     CU_CHECK(cuMemcpyDtoHAsync(&count, p->misc.p, 8, p->stream));
+    CU_CHECK(cuMemcpyDtoHAsync(&full, p->ctr.p + offsetof(Counters, table_full), 8, p->stream));
     CU_CHECK(cuStreamSynchronize(p->stream));
     if (n) *n = count;
+    // (also reports an overflow of an earlier, unsynchronised bsi_attract_table_merge_device)
+    if (full) return fail(BSI_E_CAPACITY, "attractor table overflow (raise table_log2_slots)");
     return BSI_OK;
 }
 
@@ -717,13 +721,10 @@ int bsi_attract_table_merge_device(bsi_plan *p, const void *dev_records, uint64_
     CtxGuard g(p);
     CUdeviceptr recs = (CUdeviceptr)dev_records;
     void *args[] = {&p->table.p, &p->table_log2, &recs, &n, &p->ctr.p};
-    CU_CHECK(cuMemsetD8Async(p->ctr.p + offsetof(Counters, table_full), 0, 8, p->stream));
     unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)p->n_sms * 4);
-    if ((rc = launch(p, p->f_merge, grid, 256, 0, args))) return rc;
-    Counters c;
-    if ((rc = read_counters(p, &c))) return rc;
-    if (c.table_full) return fail(BSI_E_CAPACITY, "attractor table overflow (raise table_log2_slots)");
-    return BSI_OK;
+    // asynchronous on the plan's stream: a table overflow is reported by the next
+    // bsi_attract_table_count / _read / _export_device
+    return launch(p, p->f_merge, grid, 256, 0, args);
 }
 
 // ---- trajectories (simulate, orbits) --------------------------------------------------------------

@@ -69,8 +69,11 @@ struct BsiFound {       // one lane that matched a checkpoint
     u64 idx;            // problem index
     u64 y[BSI_KW];      // the matched state (on the cycle), state code words
     u64 key[BSI_KW];    // canonical key, filled by bsi_resolve_key
+    u64 z[BSI_KW];      // state at time c0 (valid when c0 > 0)
     u32 lam;            // cycle length
     u32 c;              // time of the matched checkpoint (>= mu), relative to lp
+    u32 c0;             // a time < mu: the previous final checkpoint, or 0 (then x_0 comes from idx)
+    u32 pad;
 };
 
 struct BsiSlot {
@@ -218,7 +221,7 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // dynamic shared memory of the main kernel: the stage-2 filter words of the three checkpoint
 // slots, u32 f2[3][BSI_F2][BLOCK].  The per-thread scratch in global memory (L2-resident, sized by
 // the persistent grid) holds, per thread: 3 full checkpoints [3][N], then the detection records
-// of its 32 lanes: u32 lam[32], u32 c[32], u64 y[KW][32].
+// of its 32 lanes: u32 lam[32], u32 c[32], u32 c0[32], u64 y[KW][32], u64 z[KW][32].
 extern __shared__ __align__(16) unsigned char bsi_smem[];
 
 // full compare of a state held in local memory with a checkpoint in the scratch: lanes of
@@ -232,7 +235,9 @@ __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 
 
 // detection record of the lanes in m: cycle length, checkpoint time and the matched state code
 __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
-                                           u64 *y_s, u64 sstride) {
+                                           u64 *y_s, u64 sstride, const u32 *prev_ck, u32 prev_t) {
+    u32 *c0_s = c_s + 32ull * sstride;
+    u64 *z_s = y_s + (u64)BSI_KW * 32ull * sstride;
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
@@ -249,6 +254,19 @@ __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c,
         c_s[l * sstride] = c;
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) y_s[(k * 32 + l) * sstride] = code[k];
+        // a matched final checkpoint s >= 1 implies mu > c_(s-1) (slot s-1 stays armed and would
+        // have matched earlier): ship that state as the start of the mu walk
+        c0_s[l * sstride] = prev_ck ? prev_t : 0u;
+        if (prev_ck) {
+#pragma unroll
+            for (int k = 0; k < BSI_KW; ++k) {
+                u64 z = 0ull;
+#pragma unroll 1
+                for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
+                    z |= (u64)((prev_ck[(u64)i * sstride] >> l) & 1u) << (i & 63);
+                z_s[(k * 32 + l) * sstride] = z;
+            }
+        }
     }
 }
 
@@ -267,8 +285,8 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     u32 *const my_scratch = scratch + gtid;
     // detection records of this thread's 32 lanes (rarely written): after the 3 checkpoint slots
     u32 *const lam_s = scratch + 3ull * BSI_N * sstride + gtid;       // [32][sstride]
-    u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride]
-    u64 *const y_s = (u64 *)(scratch + (3ull * BSI_N + 64ull) * sstride) + gtid;   // [KW][32][sstride]
+    u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride], then c0 [32]
+    u64 *const y_s = (u64 *)(scratch + (3ull * BSI_N + 96ull) * sstride) + gtid;   // y, z: [2][KW][32][sstride]
     u64 dev_steps = 0, n_without = 0, ref_steps = 0;
 
     for (;;) {
@@ -322,7 +340,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
-                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s, sstride);      \
+                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s, sstride,       \
+                           (S) > 0 ? my_scratch + (u64)((S) - 1) * BSI_N * sstride : nullptr, \
+                           (S) == 1 ? st0 : st1);                                    \
             }                                                                        \
         }                                                                            \
     }
@@ -478,9 +498,12 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 for (int i = 0; i < BSI_KW; ++i) {
                     r.y[i] = y_s[(i * 32 + l) * sstride];
                     r.key[i] = r.y[i];
+                    r.z[i] = y_s[((BSI_KW + i) * 32 + l) * sstride];
                 }
                 r.lam = lam_s[l * sstride];
                 r.c = c_s[l * sstride];
+                r.c0 = c_s[(32 + l) * sstride];
+                r.pad = 0u;
                 found_q[base_f++] = r;
             }
         }
@@ -588,10 +611,11 @@ bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
 }
 
 // Exact mu, then acceptance and aggregation.  With y = x_c on the cycle, let P be the periodic
-// extension of the cycle to all times: P(j) = x_j exactly for j >= mu, so
-//     mu = first j with x_j == P(j),   P(0) = y advanced by (lambda - c mod lambda) mod lambda.
-// a* walks x_j from the problem index, b* walks P(j); three register sets rotate so that no step
-// needs a copy.  Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
+// extension of the cycle to all times: P(j) = x_j exactly for j >= mu, so for any c0 < mu
+//     mu = first j >= c0 with x_j == P(j),   P(c0) = y advanced by (lambda - (c - c0) mod lambda) mod lambda.
+// a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
+// walks P(j); three register sets rotate so that no step needs a copy.
+// Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_attractor_l,
                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
@@ -608,7 +632,7 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
         BSI_FOR_NODES(BSI_ZERO_B)
-        u32 valid = 0u, adv_max = 0u, c_max = 0u;
+        u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u;
         for (u32 l = 0; l < 32; ++l) {
             u64 q = (w << 5) + l;
             if (q < n_found) {
@@ -617,14 +641,15 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
                 for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].y[i];
                 BSI_INSERT(b, l, c_)
                 valid |= 1u << l;
-                const u32 lam = found_q[q].lam, c = found_q[q].c;
-                const u32 adv = (lam - c % lam) % lam;
+                const u32 lam = found_q[q].lam, c = found_q[q].c, c0 = found_q[q].c0;
+                const u32 adv = (lam - (c - c0) % lam) % lam;
                 aux_s[l * BSI_BLOCK + tid] = adv;
                 adv_max = max(adv_max, adv);
-                c_max = max(c_max, c);
+                c_max = max(c_max, c - c0);          // the walk is at most c - c0 steps long
+                if (c0 == 0u) from_idx |= 1u << l;
             }
         }
-        // ---- b <- P(0): advance each lane by its own number of steps --------------------------
+        // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
 #define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
         {
             u32 go_ = 0u, next_ev = 0u;
@@ -643,25 +668,39 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
             }
         }
 #undef BSI_HOLD_NODE
-        // ---- a <- x_lp from the problem index ---------------------------------------------------
+        // ---- a <- x_c0: from the problem index (c0 = 0) or the shipped checkpoint state -----------
         {
-            // the prefix macro works on (a, b): park P(0) in c meanwhile
+            // the prefix macro works on (a, b): park P(c0) in c meanwhile
 #define BSI_COPY_CB(i) c##i = b##i;
 #define BSI_COPY_BC(i) b##i = c##i;
+#define BSI_MASK_A(i) a##i &= from_idx;
             BSI_FOR_NODES(BSI_COPY_CB)
             BSI_FOR_NODES(BSI_ZERO_A)
+            if (from_idx) {
+                for (u32 l = 0; l < 32; ++l) {
+                    u64 q = (w << 5) + l;
+                    if ((from_idx >> l) & 1u) {
+                        u64 c_[BSI_KW];
+                        u64 lp_lane_ = 0;
+                        BSI_LANE_SETUP(l, found_q[q].idx, c_)
+                        (void)lp_lane_;
+                        BSI_INSERT(a, l, c_)
+                    }
+                }
+                BSI_PREFIX(BSI_LP_ORIGIN)
+                BSI_FOR_NODES(BSI_MASK_A)
+            }
             for (u32 l = 0; l < 32; ++l) {
                 u64 q = (w << 5) + l;
-                if (q < n_found) {
+                if (((valid & ~from_idx) >> l) & 1u) {
                     u64 c_[BSI_KW];
-                    u64 lp_lane_ = 0;
-                    BSI_LANE_SETUP(l, found_q[q].idx, c_)
-                    (void)lp_lane_;
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].z[i];
                     BSI_INSERT(a, l, c_)
                 }
             }
-            BSI_PREFIX(BSI_LP_ORIGIN)
             BSI_FOR_NODES(BSI_COPY_BC)
+#undef BSI_MASK_A
 #undef BSI_COPY_CB
 #undef BSI_COPY_BC
         }
@@ -714,7 +753,7 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
                 for (int i = 0; i < BSI_KW; ++i) same = same && (r->key[i] == r0.key[i]);
                 if (!same) continue;
                 todo &= ~(1u << l);
-                const u64 mu = aux_s[l * BSI_BLOCK + tid];
+                const u64 mu = (u64)r->c0 + aux_s[l * BSI_BLOCK + tid];
                 const u64 lam = r->lam;
                 if (mu + lam <= T) {                     // the loop stops at t = mu + lambda (model.py:201)
                     steps += BSI_LP_ORIGIN + mu + lam;

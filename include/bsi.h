@@ -196,7 +196,9 @@ int bsi_attract_table_read(bsi_plan *plan, bsi_attractor_rec *out, uint64_t cap,
  * records beyond the count are zeroed, n == 0 marks an empty record): the per-GPU payload of the
  * one NCCL allgather that replaces the MPI collection stage (mpi.py:296-332). */
 int bsi_attract_table_export_device(bsi_plan *plan, void *dev_out, uint64_t cap, uint64_t *n);
-/* Reduce-by-key `n` records in DEVICE memory into the table (integer adds: exact, order-free). */
+/* Reduce-by-key `n` records in DEVICE memory into the table (integer adds: exact, order-free);
+ * records with n == 0 are skipped.  Asynchronous on the plan's stream; a table overflow is
+ * reported by the next bsi_attract_table_count / _read / _export_device. */
 int bsi_attract_table_merge_device(bsi_plan *plan, const void *dev_records, uint64_t n);
 /* Orbit of `key` under the fixed-node-adjusted rules: out[lambda][key_words], key state first
  * (the rotation of attract.py:22-25).  HOST output. */
