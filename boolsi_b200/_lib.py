@@ -30,7 +30,7 @@ EXPORTS = [
     'bsi_attract_table_clear', 'bsi_attract_table_count', 'bsi_attract_table_read',
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
-    'bsi_measure_update_rate',
+    'bsi_measure_update_rate', 'bsi_release_cached_memory',
 ]
 
 
@@ -373,6 +373,10 @@ class Plan:
                                    _ptr(hit_index), _ptr(hit_t), capacity, C.byref(got),
                                    C.byref(st)))
         return hit_index[:got.value], hit_t[:got.value], st.as_dict()
+
+
+def release_cached_memory():
+    check(lib().bsi_release_cached_memory())
 
 
 def device_count():

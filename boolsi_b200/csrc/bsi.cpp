@@ -14,6 +14,7 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,18 @@ int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+
+// BSI_DEBUG_TIMING=1: host-side stage times on stderr
+struct StageTimer {
+    bool on = getenv("BSI_DEBUG_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bsi] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // ---- CUDA driver API, bound at first use -------------------------------------------------------
 #define BSI_STR2(x) #x
@@ -145,6 +158,19 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+// The primary context of a device is retained once and kept for the life of the process (as the
+// CUDA runtime does): releasing the last reference would tear the context down, and the next plan
+// would pay hundreds of ms to bring it back.
+std::mutex g_dev_mu;
+std::map<int, CUcontext> g_ctx;
+
+// Freed device buffers >= 1 MiB are parked per device and reused by later plans (the found queue
+// of a 2^26-state chunk is 3 GB; cuMemAlloc/cuMemFree of that size cost tens of ms).
+struct Parked { CUdeviceptr p; size_t bytes; };
+std::map<int, std::vector<Parked>> g_pool;
+size_t g_pool_bytes = 0;
+constexpr size_t kPoolMinBytes = (size_t)1 << 20, kPoolMaxBytes = (size_t)24 << 30;
+
 }  // namespace
 
 struct bsi_plan {
@@ -183,11 +209,67 @@ struct CtxGuard {
     }
 };
 
+int device_context(int device, CUdevice *dev, CUcontext *ctx) {
+    CU_CHECK(cuDeviceGet(dev, device));
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    auto it = g_ctx.find(device);
+    if (it == g_ctx.end()) {
+        CUcontext c = nullptr;
+        CU_CHECK(cuDevicePrimaryCtxRetain(&c, *dev));
+        it = g_ctx.emplace(device, c).first;
+    }
+    *ctx = it->second;
+    return BSI_OK;
+}
+
+void give_back(int device, DevBuf &b) {
+    if (!b.p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (b.bytes >= kPoolMinBytes && g_pool_bytes + b.bytes <= kPoolMaxBytes) {
+            g_pool[device].push_back({b.p, b.bytes});
+            g_pool_bytes += b.bytes;
+            b.p = 0;
+            b.bytes = 0;
+            return;
+        }
+    }
+    cu().p_cuMemFree(b.p);
+    b.p = 0;
+    b.bytes = 0;
+}
+
 int ensure(bsi_plan *p, DevBuf &b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return BSI_OK;
-    if (b.p) { cu().p_cuMemFree(b.p); b.p = 0; b.bytes = 0; }
+    give_back(p->device, b);
     size_t want = std::max<size_t>(bytes, 256);
+    if (want >= kPoolMinBytes) {
+        // best fit among the parked buffers of this device, wasting at most 2x
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        auto &v = g_pool[p->device];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); ++i)
+            if (v[i].bytes >= want && v[i].bytes <= 2 * want && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+        if (best >= 0) {
+            b.p = v[best].p;
+            b.bytes = v[best].bytes;
+            g_pool_bytes -= v[best].bytes;
+            v.erase(v.begin() + best);
+            return BSI_OK;
+        }
+    }
     CUresult r = cu().p_cuMemAlloc(&b.p, want);
+    if (r == CUDA_ERROR_OUT_OF_MEMORY) {
+        // drop everything parked on this device and retry once
+        std::vector<Parked> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_dev_mu);
+            drop.swap(g_pool[p->device]);
+            for (auto &q : drop) g_pool_bytes -= q.bytes;
+        }
+        for (auto &q : drop) cu().p_cuMemFree(q.p);
+        r = cu().p_cuMemAlloc(&b.p, want);
+    }
     if (r != CUDA_SUCCESS) {
         b.p = 0;
         return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? BSI_E_NOMEM : BSI_E_CUDA,
@@ -255,9 +337,11 @@ std::vector<int> choose_filter(const bsi::Model &m, int want, std::vector<int> *
 }
 
 int compile_plan(bsi_plan *p) {
+    StageTimer tm;
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
     std::vector<int> filter2;
     std::vector<int> filter = choose_filter(p->m, f_nodes, &filter2, 12);
+    tm.lap("choose_filter");
     p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
     if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
     // register cap of the trajectory kernels: 3 warps per scheduler when the state fits (measured
@@ -266,6 +350,7 @@ int compile_plan(bsi_plan *p) {
     p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, p->info);
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
+    tm.lap("generate source");
 
     // in-process cache: the same network + space + mode specialises to the same source
     static std::mutex cache_mu;
@@ -316,16 +401,18 @@ int load_plan(bsi_plan *p, int device) {
     int count = 0;
     CU_CHECK(cuDeviceGetCount(&count));
     if (device < 0 || device >= count) return fail(BSI_E_CUDA, "device %d out of range (%d devices)", device, count);
+    StageTimer tm;
     p->device = device;
-    CU_CHECK(cuDeviceGet(&p->dev, device));
-    CU_CHECK(cuDevicePrimaryCtxRetain(&p->ctx, p->dev));
+    if (int rc0 = device_context(device, &p->dev, &p->ctx)) return rc0;
     CtxGuard g(p);
+    tm.lap("context");
     int major = 0, minor = 0;
     CU_CHECK(cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, p->dev));
     CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
     if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
     CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
     CU_CHECK(cuModuleLoadData(&p->mod, p->cubin.data()));
+    tm.lap("cuModuleLoadData");
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
     p->stream = p->own_stream;
     CU_CHECK(cuModuleGetFunction(&p->f_traj, p->mod, "bsi_trajectories"));
@@ -361,6 +448,7 @@ int load_plan(bsi_plan *p, int device) {
     if (rc) return rc;
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
     CU_CHECK(cuStreamSynchronize(p->stream));
+    tm.lap("functions + table alloc");
     return BSI_OK;
 }
 
@@ -444,20 +532,41 @@ int bsi_plan_create_offline(const bsi_network_desc *network, const bsi_space_des
 
 void bsi_plan_destroy(bsi_plan *p) {
     if (!p) return;
+    StageTimer tm;
     if (p->ctx && cu().ok) {
         {
             CtxGuard g(p);
             if (p->stream) cu().p_cuStreamSynchronize(p->stream);
             for (DevBuf *b : {&p->ctr, &p->table, &p->found_q, &p->retry_q[0], &p->retry_q[1], &p->scratch,
                               &p->misc, &p->misc2, &p->misc3})
-                if (b->p) cu().p_cuMemFree(b->p);
+                give_back(p->device, *b);
+            tm.lap("destroy: buffers");
             for (CUevent e : p->events) cu().p_cuEventDestroy(e);
             if (p->own_stream) cu().p_cuStreamDestroy(p->own_stream);
             if (p->mod) cu().p_cuModuleUnload(p->mod);
+            tm.lap("destroy: module/stream");
         }
-        cu().p_cuDevicePrimaryCtxRelease(p->dev);
     }
     delete p;
+}
+
+int bsi_release_cached_memory(void) {
+    if (!cu().ok) return BSI_OK;
+    std::map<int, std::vector<Parked>> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        drop.swap(g_pool);
+        g_pool_bytes = 0;
+    }
+    for (auto &kv : drop) {
+        auto it = g_ctx.find(kv.first);
+        if (it == g_ctx.end()) continue;
+        if (cu().p_cuCtxPushCurrent(it->second) != CUDA_SUCCESS) continue;
+        for (auto &q : kv.second) cu().p_cuMemFree(q.p);
+        CUcontext c;
+        cu().p_cuCtxPopCurrent(&c);
+    }
+    return BSI_OK;
 }
 
 int bsi_plan_n_problems(const bsi_plan *p, uint64_t *n) {
@@ -976,9 +1085,8 @@ int bsi_measure_lop3_peak(int device, double *lop3_per_s, double *sm_clock_mhz, 
     int count = 0;
     CU_CHECK(cuDeviceGetCount(&count));
     if (device < 0 || device >= count) return fail(BSI_E_CUDA, "device out of range");
-    CU_CHECK(cuDeviceGet(&tmp.dev, device));
-    CU_CHECK(cuDevicePrimaryCtxRetain(&tmp.ctx, tmp.dev));
-    int rc = BSI_OK;
+    int rc = device_context(device, &tmp.dev, &tmp.ctx);
+    if (rc) return rc;
     {
         CtxGuard g(&tmp);
         CUmodule mod = nullptr;
@@ -1023,7 +1131,6 @@ int bsi_measure_lop3_peak(int device, double *lop3_per_s, double *sm_clock_mhz, 
         if (s) cu().p_cuStreamDestroy(s);
         if (mod) cu().p_cuModuleUnload(mod);
     }
-    cu().p_cuDevicePrimaryCtxRelease(tmp.dev);
     tmp.ctx = nullptr;
     return rc;
 }
