@@ -344,9 +344,9 @@ int compile_plan(bsi_plan *p) {
     tm.lap("choose_filter");
     p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
     if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
-    // register cap of the trajectory kernels: 3 warps per scheduler when the state fits (measured
-    // best for N = 64), otherwise whatever the block size allows
-    const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : (p->m.n <= 64 && p->block == 64 ? 6 : 1);
+    // register cap of the trajectory kernels: none by default (min_blocks = 6, i.e. 168 registers and
+    // 3 warps per scheduler, measured 1.7 % faster at N = 64 but spills filter words in the hot loop)
+    const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
     p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, p->info);
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
