@@ -30,7 +30,7 @@ EXPORTS = [
     'bsi_attract_table_clear', 'bsi_attract_table_count', 'bsi_attract_table_read',
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
-    'bsi_measure_update_rate', 'bsi_release_cached_memory',
+    'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
         L.bsi_attract_table_read.argtypes = [p, p, u64, C.POINTER(u64)]
         L.bsi_attract_table_export_device.argtypes = [p, p, u64, C.POINTER(u64)]
         L.bsi_attract_table_merge_device.argtypes = [p, p, u64]
+        L.bsi_attract_table_export_payload.argtypes = [p, p, u64]
         L.bsi_attractor_states.argtypes = [p, p, u64, p]
         L.bsi_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_simulate_list.argtypes = [p, p, u64, u64, p, C.POINTER(RunStats)]
@@ -334,6 +335,10 @@ class Plan:
         check(lib().bsi_attract_table_export_device(self._h, C.c_void_p(dev_ptr), int(capacity),
                                                     C.byref(n)))
         return n.value
+
+    def table_export_payload(self, dev_ptr, capacity):
+        """Header record + records into a device buffer of `capacity` records, no host sync."""
+        check(lib().bsi_attract_table_export_payload(self._h, C.c_void_p(dev_ptr), int(capacity)))
 
     def table_merge_device(self, dev_ptr, n):
         check(lib().bsi_attract_table_merge_device(self._h, C.c_void_p(dev_ptr), int(n)))

@@ -69,8 +69,10 @@ class AttractEngine:
         if self._gather is None:
             self._gather = {}
         everyone, headers = exchange_tables(
-            lambda buf: self.plan.table_export_device(buf.data_ptr(), buf.shape[0]),
-            (st['steps'], st['n_found'], st['n_without']), self.world, 'cuda', buffers=self._gather)
+            lambda buf: self.plan.table_export_payload(buf.data_ptr(), buf.shape[0]),
+            self.world, 'cuda', buffers=self._gather)
+        if int(headers[:, 5].max()):
+            raise _lib.BsiError(-4, 'attractor table overflow on some rank (raise table_log2_slots)')
         # fold the OTHER ranks' records into this rank's table (header rows and unused rows have
         # n == 0 and are skipped by the merge kernel): two launches, no host synchronisation
         rows = everyone.shape[1]

@@ -768,13 +768,16 @@ int bsi_attract_table_clear(bsi_plan *p) {
     return BSI_OK;
 }
 
-static int export_table(bsi_plan *p, CUdeviceptr out, uint64_t cap, uint64_t *n) {
+static int export_table(bsi_plan *p, CUdeviceptr out, uint64_t cap, uint64_t *n, CUdeviceptr header,
+                        bool sync) {
     int rc = ensure(p, p->misc, 256);
     if (rc) return rc;
-    CU_CHECK(cuMemsetD8Async(p->misc.p, 0, 8, p->stream));
+    CU_CHECK(cuMemsetD8Async(p->misc.p, 0, 16, p->stream));     // [0] record count, [1] blocks done
     if (out && cap) CU_CHECK(cuMemsetD8Async(out, 0, cap * sizeof(bsi_attractor_rec), p->stream));
-    void *args[] = {&p->table.p, &p->table_log2, &out, &cap, &p->misc.p};
+    CUdeviceptr done = p->misc.p + 8;
+    void *args[] = {&p->table.p, &p->table_log2, &out, &cap, &p->misc.p, &header, &p->ctr.p, &done};
     if ((rc = launch(p, p->f_export, (unsigned)(p->n_sms * 4), 256, 0, args))) return rc;
+    if (!sync) return BSI_OK;
     uint64_t count = 0, full = 0;
     CU_CHECK(cuMemcpyDtoHAsync(&count, p->misc.p, 8, p->stream));
     CU_CHECK(cuMemcpyDtoHAsync(&full, p->ctr.p + offsetof(Counters, table_full), 8, p->stream));
@@ -789,7 +792,7 @@ int bsi_attract_table_count(bsi_plan *p, uint64_t *n) {
     int rc = need_device(p, BSI_MODE_ATTRACT);
     if (rc) return rc;
     CtxGuard g(p);
-    return export_table(p, 0, 0, n);
+    return export_table(p, 0, 0, n, 0, true);
 }
 
 int bsi_attract_table_read(bsi_plan *p, bsi_attractor_rec *out, uint64_t cap, uint64_t *n) {
@@ -798,7 +801,7 @@ int bsi_attract_table_read(bsi_plan *p, bsi_attractor_rec *out, uint64_t cap, ui
     CtxGuard g(p);
     if ((rc = ensure(p, p->misc2, std::max<uint64_t>(cap, 1) * sizeof(bsi_attractor_rec)))) return rc;
     uint64_t count = 0;
-    if ((rc = export_table(p, p->misc2.p, cap, &count))) return rc;
+    if ((rc = export_table(p, p->misc2.p, cap, &count, 0, true))) return rc;
     if (n) *n = count;
     if (count > cap) return fail(BSI_E_CAPACITY, "attractor table holds %llu records, buffer %llu",
                                  (unsigned long long)count, (unsigned long long)cap);
@@ -815,11 +818,20 @@ int bsi_attract_table_export_device(bsi_plan *p, void *dev_out, uint64_t cap, ui
     if (!dev_out) return fail(BSI_E_ARG, "null device buffer");
     CtxGuard g(p);
     uint64_t count = 0;
-    if ((rc = export_table(p, (CUdeviceptr)dev_out, cap, &count))) return rc;
+    if ((rc = export_table(p, (CUdeviceptr)dev_out, cap, &count, 0, true))) return rc;
     if (n) *n = count;
     if (count > cap) return fail(BSI_E_CAPACITY, "attractor table holds %llu records, buffer %llu",
                                  (unsigned long long)count, (unsigned long long)cap);
     return BSI_OK;
+}
+
+int bsi_attract_table_export_payload(bsi_plan *p, void *dev_out, uint64_t cap) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (!dev_out || cap < 1) return fail(BSI_E_ARG, "need a device buffer of at least one record");
+    CtxGuard g(p);
+    CUdeviceptr base = (CUdeviceptr)dev_out;
+    return export_table(p, base + sizeof(bsi_attractor_rec), cap - 1, nullptr, base, false);
 }
 
 int bsi_attract_table_merge_device(bsi_plan *p, const void *dev_records, uint64_t n) {

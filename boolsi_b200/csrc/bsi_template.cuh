@@ -780,8 +780,12 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
 }
 
 // ---- attractor table: export / merge ------------------------------------------------------------
+// Compacts the table into out[0 .. cap).  With `header` set, the last block to finish also writes
+// one header record there: key = {count, trajectory-steps, accepted, without}, n = 0 (so that a
+// merge skips it) -- the per-rank payload of the all_gather needs no host round trip.
 extern "C" __global__ void bsi_table_export(const BsiSlot *table, u32 log2_slots, BsiRec *out,
-                                            u64 cap, u64 *count) {
+                                            u64 cap, u64 *count, BsiRec *header,
+                                            const BsiCounters *ctr, u32 *blocks_done) {
     const u64 n_slots = (u64)1 << log2_slots;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots;
          i += (u64)gridDim.x * blockDim.x) {
@@ -796,6 +800,22 @@ extern "C" __global__ void bsi_table_export(const BsiSlot *table, u32 log2_slots
                 r.n = table[i].n; r.s1 = table[i].s1; r.s2 = table[i].s2; r.lam = table[i].lam;
                 out[pos] = r;
             }
+        }
+    }
+    if (header) {
+        __shared__ u32 last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = atomicAdd(blocks_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            BsiRec h;
+            h.key[0] = *((volatile u64 *)count);
+            h.key[1] = ctr->steps; h.key[2] = ctr->n_accepted; h.key[3] = ctr->n_without;
+            h.n = 0ull; h.s1 = ctr->table_full; h.s2 = 0ull; h.lam = 0ull;
+            *header = h;
         }
     }
 }

@@ -199,6 +199,11 @@ int bsi_attract_table_read(bsi_plan *plan, bsi_attractor_rec *out, uint64_t cap,
  * records beyond the count are zeroed, n == 0 marks an empty record): the per-GPU payload of the
  * one NCCL allgather that replaces the MPI collection stage (mpi.py:296-332). */
 int bsi_attract_table_export_device(bsi_plan *plan, void *dev_out, uint64_t cap, uint64_t *n);
+/* The same without any host round trip (asynchronous on the plan's stream): dev_out[0] becomes a
+ * HEADER record -- key = {records in the table, trajectory-steps, accepted, without} of the last
+ * bsi_attract_run, n = 0, sum_l = table-overflow flag -- and dev_out[1 .. cap) the records
+ * (truncated if the table holds more than cap - 1; the header still carries the true count). */
+int bsi_attract_table_export_payload(bsi_plan *plan, void *dev_out, uint64_t cap);
 /* Reduce-by-key `n` records in DEVICE memory into the table (integer adds: exact, order-free);
  * records with n == 0 are skipped.  Asynchronous on the plan's stream; a table overflow is
  * reported by the next bsi_attract_table_count / _read / _export_device. */

@@ -177,3 +177,31 @@ def test_no_device_plan_cannot_run():
     with _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True) as plan:
         with pytest.raises(_lib.BsiError):
             plan.attract_run(0, 16, 10, inf)
+
+
+def test_two_shards_export_payload_and_merge_equal_the_whole():
+    """The N>1 data path on one GPU: two plans take the two halves of the index space, export
+    header + records to device buffers (no host round trip) and fold each other's records in."""
+    import torch
+    from boolsi_b200.problems import shard_range
+    case = [c for c in goldenlib.cases('attract') if c['name'] == 'attract_rnd20k2s3_f12_tinf_ainf'][0]
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    want = [(k, n, s1, s2, len(cyc)) for k, n, s1, s2, cyc in goldenlib.expected_attractor_rows(case)]
+    plans = [_lib.Plan(pk, _lib.MODE_ATTRACT) for _ in range(2)]
+    bufs = [torch.zeros((257, 8), dtype=torch.int64, device='cuda') for _ in range(2)]
+    stats = []
+    for r, (plan, buf) in enumerate(zip(plans, bufs)):
+        lo, hi = shard_range(pk.n_problems, r, 2)
+        stats.append(plan.attract_run(lo, hi, a['max_t'], a['max_attractor_l']))
+        plan.table_export_payload(buf.data_ptr(), buf.shape[0])
+    torch.cuda.synchronize()
+    headers = [b[0].cpu().tolist() for b in bufs]
+    for h, st, plan in zip(headers, stats, plans):
+        assert h[:6] == [plan.table_count(), st['steps'], st['n_found'], st['n_without'], 0, 0]
+    assert sum(h[1] for h in headers) == case['expected']['steps']
+    plans[0].table_merge_device(bufs[1].data_ptr(), bufs[1].shape[0])     # header row is skipped (n = 0)
+    plans[1].table_merge_device(bufs[0].data_ptr(), bufs[0].shape[0])
+    for plan in plans:
+        assert _table_rows(plan) == want
+        plan.close()

@@ -71,14 +71,13 @@ def _gloo_worker(rank, world, port, n_free, capacity, out_dir):
     rec = coracle.attract_records(sp, inf, inf, lo, hi, n_threads=1)
     mine = _records_from_table(coracle.attract_table(rec, sp.kw), sp.kw)
 
-    def export(buf):
-        m = min(len(mine), buf.shape[0])
+    def fill(buf):
+        m = min(len(mine), buf.shape[0] - 1)
         buf.zero_()
-        buf[:m].copy_(torch.from_numpy(mine[:m]))
-        return len(mine)
+        buf[0, :4] = torch.tensor([len(mine), rec['steps'], int(rec['found'].sum()), 0])
+        buf[1:1 + m].copy_(torch.from_numpy(mine[:m]))
 
-    everyone, headers = exchange_tables(export, (rec['steps'], int(rec['found'].sum()), 0), world, 'cpu',
-                                        capacity=capacity)
+    everyone, headers = exchange_tables(fill, world, 'cpu', capacity=capacity)
     merged = {}
     for r in range(world):
         for row in everyone[r, 1:1 + int(headers[r, 0])].numpy():
