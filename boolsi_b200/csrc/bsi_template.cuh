@@ -227,9 +227,11 @@ extern __shared__ __align__(16) unsigned char bsi_smem[];
 // full compare of a state held in local memory with a checkpoint in the scratch: lanes of
 // `cand` whose N words all agree
 __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 sstride, u32 cand) {
+    // (a lane that passed both filters almost always matches, so there is no early exit; the
+    //  partial unroll keeps several independent L2 loads in flight)
     u32 acc = ~cand;
-#pragma unroll 1
-    for (int i = 0; i < BSI_N && acc != 0xFFFFFFFFu; ++i) acc |= xs[i] ^ ck[(u64)i * sstride];
+#pragma unroll 8
+    for (int i = 0; i < BSI_N; ++i) acc |= xs[i] ^ ck[(u64)i * sstride];
     return ~acc;
 }
 
@@ -246,7 +248,7 @@ __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c,
         for (int k = 0; k < BSI_KW; ++k) code[k] = 0ull;
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) {
-#pragma unroll 1
+#pragma unroll 8
             for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
                 code[k] |= (u64)((xs[i] >> l) & 1u) << (i & 63);
         }
@@ -261,7 +263,7 @@ __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c,
 #pragma unroll
             for (int k = 0; k < BSI_KW; ++k) {
                 u64 z = 0ull;
-#pragma unroll 1
+#pragma unroll 8
                 for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
                     z |= (u64)((prev_ck[(u64)i * sstride] >> l) & 1u) << (i & 63);
                 z_s[(k * 32 + l) * sstride] = z;
