@@ -27,9 +27,9 @@ UNIT = 'trajectory-steps/s'
 N_NODES, K_IN, SEED, N_FREE, MAX_T = 64, 3, 0, 26, 1000
 
 
-def workload(n_free=N_FREE):
+def workload(n_free=N_FREE, seed=SEED):
     from boolsi_b200 import synth
-    cfg = synth.random_attract_problem(N_NODES, K_IN, SEED, n_free=n_free)
+    cfg = synth.random_attract_problem(N_NODES, K_IN, seed, n_free=n_free)
     return cfg, (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
                  cfg['simulation problem variations'])
 
@@ -289,6 +289,22 @@ def run_gpu(a):
                        'trajectory_steps': res['steps_total']},
         }
         if world == 1 and not a.no_cpu:
+            # the same job on the other two seeded networks SURVEY.md section 8d names (not the headline)
+            others = {}
+            for seed in (1, 2):
+                _, oargs = workload(a.n_free, seed)
+                oeng = AttractEngine(*oargs, device=local)
+                oeng.run(MAX_T, inf)
+                ost = [oeng.run(MAX_T, inf) for _ in range(3)]
+                oops = oeng.plan.op_counts()
+                best = min(ost, key=lambda x: x['ms_total'])
+                others['seed%d' % seed] = {
+                    'value': best['steps'] / (best['ms_total'] * 1e-3), 'ms': best['ms_total'],
+                    'found_fraction': best['n_found'] / best['n_problems'],
+                    'whole_step_frac': best['steps'] * (oops['update_lop3'] + oops['compare_lop3']) / 32.0
+                    / (best['ms_total'] * 1e-3) / peak['lop3_per_s']}
+                oeng.close()
+            line['other_seeds'] = others
             cores = os.cpu_count() or 1
             line['cpu_baseline'] = cpu_python_port(args, n, 12.0, cores)
             line['cpu_baseline_c'] = cpu_c_port(args, n, 8.0, cores)

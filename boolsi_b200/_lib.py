@@ -31,6 +31,7 @@ EXPORTS = [
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
     'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
+    'bsi_attractor_states_batch',
 ]
 
 
@@ -121,6 +122,7 @@ def lib():
         L.bsi_attract_table_merge_device.argtypes = [p, p, u64]
         L.bsi_attract_table_export_payload.argtypes = [p, p, u64]
         L.bsi_attractor_states.argtypes = [p, p, u64, p]
+        L.bsi_attractor_states_batch.argtypes = [p, p, u64, u64, p]
         L.bsi_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_simulate_list.argtypes = [p, p, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_target_run.argtypes = [p, u64, u64, u64, p, p, u64, C.POINTER(u64),
@@ -349,6 +351,25 @@ class Plan:
         out = np.zeros((int(lam), self.kw), np.uint64)
         check(lib().bsi_attractor_states(self._h, _ptr(kwords), int(lam), _ptr(out)))
         return [code_from_words(row) for row in out]
+
+    def attractor_states_batch(self, keys_and_lams):
+        """[(key, lam), ...] -> [[state codes, key first], ...]; one launch per power-of-two
+        length class so that a long cycle does not inflate the buffers of the short ones."""
+        out = [None] * len(keys_and_lams)
+        groups = {}
+        for pos, (key, lam) in enumerate(keys_and_lams):
+            groups.setdefault(max(1, int(lam) - 1).bit_length(), []).append(pos)
+        for _, members in sorted(groups.items()):
+            n_states = max(int(keys_and_lams[pos][1]) for pos in members)
+            keys = np.zeros((len(members), self.kw), np.uint64)
+            for row, pos in enumerate(members):
+                keys[row] = words_from_code(int(keys_and_lams[pos][0]), self.kw)
+            buf = np.zeros((len(members), n_states, self.kw), np.uint64)
+            check(lib().bsi_attractor_states_batch(self._h, _ptr(keys), len(members), n_states, _ptr(buf)))
+            for row, pos in enumerate(members):
+                lam = int(keys_and_lams[pos][1])
+                out[pos] = [code_from_words(w) for w in buf[row, :lam]]
+        return out
 
     # ---- simulate / target -----------------------------------------------------------------
     def simulate_run(self, idx_begin, idx_end, max_t):

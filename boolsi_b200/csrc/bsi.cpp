@@ -928,6 +928,16 @@ int bsi_attractor_states(bsi_plan *p, const uint64_t *key, uint64_t lambda, uint
     return run_trajectories(p, 0, nullptr, key, 1, lambda - 1, out, nullptr);
 }
 
+int bsi_attractor_states_batch(bsi_plan *p, const uint64_t *keys, uint64_t n, uint64_t n_states,
+                               uint64_t *out) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (n == 0) return BSI_OK;
+    if (!keys || !out || n_states == 0) return fail(BSI_E_ARG, "bad arguments");
+    CtxGuard g(p);
+    return run_trajectories(p, 0, nullptr, keys, n, n_states - 1, out, nullptr);
+}
+
 // ---- target ---------------------------------------------------------------------------------------
 int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
                    uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,

@@ -211,6 +211,10 @@ int bsi_attract_table_merge_device(bsi_plan *plan, const void *dev_records, uint
 /* Orbit of `key` under the fixed-node-adjusted rules: out[lambda][key_words], key state first
  * (the rotation of attract.py:22-25).  HOST output. */
 int bsi_attractor_states(bsi_plan *plan, const uint64_t *key, uint64_t lambda, uint64_t *out);
+/* The same for `n` keys in one launch, `n_states` states each (a state sequence longer than the
+ * attractor just wraps around): keys[n][key_words] in, out[n][n_states][key_words].  HOST buffers. */
+int bsi_attractor_states_batch(bsi_plan *plan, const uint64_t *keys, uint64_t n, uint64_t n_states,
+                               uint64_t *out);
 
 /* ---- simulate (replaces simulate_master's simulation stage, simulate.py:46-78) ------------- */
 /* states_out (HOST): [idx_end - idx_begin][max_t + 1][key_words], plain iteration with masks. */
