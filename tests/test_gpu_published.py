@@ -110,3 +110,29 @@ def test_cambium2_attractors_csv_is_byte_identical_to_the_published_example(tmp_
         assert (g[0], g[1], g[4]) == (w[0], w[1], w[4])
         assert math.isclose(float(g[2]), float(w[2]), rel_tol=1e-12)
         assert math.isclose(float(g[3]), float(w[3]), rel_tol=1e-9)
+
+
+def test_cambium2_node_correlations_match_the_published_csv():
+    """BASELINE.json configs[2]: attract cambium2 over all 2^30 initial states WITH the attractor
+    node-correlation analysis (reference cli.py:263-276 -> attractor_analysis.py, output.py:868)."""
+    from boolsi_b200 import analysis
+    pub = codec.load('published.json')
+    node_names, preds, tts = codec.decode_network(codec.load('networks.json')['networks']['cambium'])
+    origin, variations = codec.decode_problem(pub['cambium2_problem'], NodeStateRange)
+    n = pub['cambium2_n_problems']
+    db = boolsi_b200.ResultStore()
+    boolsi_b200.attract_master(_Comm(), 100, origin, variations, preds, tts, inf, inf, n, True, db,
+                               False, None)
+    rho, p = analysis.find_node_correlations(db)
+    text = analysis.node_correlations_csv(rho, p, 0.05, node_names)       # default --p-value 0.05
+    got = list(csv.reader(io.StringIO(text)))
+    want = list(csv.reader(io.StringIO(_published('output8_cambium2/node_correlations.csv'))))
+    assert got[0] == want[0] and len(got) == len(want)
+    by_pair = {(r[0], r[1]): r for r in got[1:]}
+    for w in want[1:]:
+        g = by_pair[(w[0], w[1])]
+        for gv, wv in zip(g[2:], w[2:]):
+            if wv == 'nan':
+                assert gv == 'nan'
+            else:
+                assert math.isclose(float(gv), float(wv), rel_tol=1e-9, abs_tol=1e-300)
