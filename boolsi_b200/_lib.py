@@ -63,7 +63,8 @@ class PlanOpts(C.Structure):
     _fields_ = [('first_horizon', C.c_uint32), ('filter_nodes', C.c_uint32),
                 ('table_log2_slots', C.c_uint32), ('chunk_log2', C.c_uint32),
                 ('keep_source', C.c_uint32), ('block_threads', C.c_uint32),
-                ('min_blocks', C.c_uint32), ('reserved', C.c_uint32 * 9)]
+                ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
+                ('reserved', C.c_uint32 * 8)]
 
 
 class RunStats(C.Structure):
@@ -73,7 +74,10 @@ class RunStats(C.Structure):
                 ('ms_resolve', C.c_double), ('reserved', C.c_uint64 * 6)]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != 'reserved'}
+        d = {name: getattr(self, name) for name, _ in self._fields_ if name != 'reserved'}
+        if self.reserved[0] or self.reserved[1]:
+            d['debug'] = list(self.reserved[:4])
+        return d
 
 
 ATTRACTOR_REC = np.dtype([('key', np.uint64, (KEY_WORDS_MAX,)), ('n', np.uint64),

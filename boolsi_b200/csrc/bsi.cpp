@@ -116,7 +116,7 @@ struct Counters {
 constexpr size_t kPerRoundBytes = 5 * sizeof(uint64_t);
 constexpr int kMaxCk = 72;
 struct Sched {
-    uint32_t n_ck, end;
+    uint32_t n_ck, end, first_final, pad;
     uint32_t ck_time[kMaxCk];
     uint32_t ck_slot[kMaxCk];
 };
@@ -150,6 +150,7 @@ Sched make_sched(uint64_t H) {
         first = false;
     }
     s.end = (uint32_t)(H + max_gap);
+    s.first_final = (uint32_t)c1;
     return s;
 }
 
@@ -347,7 +348,7 @@ int compile_plan(bsi_plan *p) {
     // register cap of the trajectory kernels: none by default (min_blocks = 6, i.e. 168 registers and
     // 3 warps per scheduler, measured 1.7 % faster at N = 64 but spills filter words in the hot loop)
     const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
-    p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, p->info);
+    p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info);
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
     tm.lap("generate source");
@@ -423,7 +424,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mod, "bsi_resolve_mu"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mod, "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mod, "bsi_table_merge"));
-        p->main_smem = (size_t)3 * p->info.filter2_nodes * p->block * 4;
+        p->main_smem = (size_t)3 * p->m.n * p->block * 4;      // the three checkpoint slots
         if (p->main_smem > 48 * 1024) {
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
             CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
@@ -661,7 +662,7 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
     const size_t found_bytes = 24 + 24 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    const size_t scratch_bytes = (size_t)main_grid * p->block * (3 * p->m.n + 96 + 128 * p->m.kw) * sizeof(uint32_t);
+    const size_t scratch_bytes = (size_t)main_grid * p->block * (96 + 128 * p->m.kw) * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
@@ -747,6 +748,7 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
     st.steps = c.steps;
     st.device_steps = c.device_steps;
     st.launches = p->launches - launches0;
+    for (int k = 0; k < 4; ++k) st.reserved[k] = c.pad[k];      // debug_stats counters
     if ((rc = elapsed(tm.e0, tm.e1, &st.ms_total))) return rc;
     for (auto &pr : tm.main) if ((rc = elapsed(pr.first, pr.second, &st.ms_main))) return rc;
     for (auto &pr : tm.resolve) if ((rc = elapsed(pr.first, pr.second, &st.ms_resolve))) return rc;

@@ -329,13 +329,14 @@ inline std::string node_list_macro(const std::string &name, int n) {
 // The macro header.  `filter` = nodes of the cheap pre-compare, in order.
 inline std::string generate_header(const Model &m, const std::vector<int> &filter,
                                    const std::vector<int> &filter2, int block_threads,
-                                   int min_blocks, GenInfo &info) {
+                                   int min_blocks, int debug_stats, GenInfo &info) {
     std::ostringstream o;
     const int n = m.n;
     o << "// generated by libbsi for a " << n << "-node network\n";
     o << "#define BSI_N " << n << "\n#define BSI_KW " << m.kw << "\n";
     o << "#define BSI_BLOCK " << block_threads << "\n";
     o << "#define BSI_MIN_BLOCKS " << min_blocks << "\n";
+    o << "#define BSI_STATS " << (debug_stats ? 1 : 0) << "\n";
     o << "#define BSI_MODE " << m.mode << "\n";
     o << "#define BSI_LANES_UNIFORM " << (m.lanes_uniform ? 1 : 0) << "\n";
     o << "#define BSI_LP_ORIGIN " << m.lp_origin << "ull\n";
@@ -466,12 +467,9 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         o << " }\n#define BSI_F2 " << std::max<size_t>(1, filter2.size()) << "\n";
         o << "#define BSI_CMP_FILTER2_MEM(acc, X, P, S) {";
         for (size_t g = 0; g < filter2.size(); ++g)
-            o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << g << " * (S)]);";
-        o << " }\n#define BSI_STORE_FILTER2(X, P, S) {";
-        for (size_t g = 0; g < filter2.size(); ++g)
-            o << " (P)[" << g << " * (S)] = X##" << filter2[g] << ";";
+            o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
-        for (int i = 0; i < n; ++i) o << " (P)[(unsigned long long)" << i << " * (S)] = X##" << i << ";";
+        for (int i = 0; i < n; ++i) o << " (P)[" << i << " * (S)] = X##" << i << ";";
         o << " }\n#define BSI_DUMP(X, A) {";
         for (int i = 0; i < n; ++i) o << " (A)[" << i << "] = X##" << i << ";";
         o << " }\n";

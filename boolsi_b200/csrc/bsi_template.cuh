@@ -61,6 +61,8 @@ struct BsiCounters {
 struct BsiSched {       // checkpoint schedule of one detection round (times relative to lp)
     u32 n_ck;
     u32 end;            // last compared time
+    u32 first_final;    // time of the first final checkpoint (earlier ones are overwritten)
+    u32 pad;
     u32 ck_time[BSI_MAX_CK];
     u32 ck_slot[BSI_MAX_CK];
 };
@@ -218,31 +220,41 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // ---------------------------------------------------------------------------------------------
 #if BSI_MODE == 1
 
-// dynamic shared memory of the main kernel: the stage-2 filter words of the three checkpoint
-// slots, u32 f2[3][BSI_F2][BLOCK].  The per-thread scratch in global memory (L2-resident, sized by
-// the persistent grid) holds, per thread: 3 full checkpoints [3][N], then the detection records
-// of its 32 lanes: u32 lam[32], u32 c[32], u32 c0[32], u64 y[KW][32], u64 z[KW][32].
+// dynamic shared memory of the main kernel: the three checkpoint slots in full,
+// u32 ck[3][N][BLOCK] (48 KB per 64-thread block at N = 64; four blocks per SM fit).  The
+// per-thread scratch in global memory (sized by the persistent grid) only holds the detection
+// records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32], u64 y[KW][32], u64 z[KW][32].
 extern __shared__ __align__(16) unsigned char bsi_smem[];
 
 // full compare of a state held in local memory with a checkpoint in the scratch: lanes of
 // `cand` whose N words all agree
-__device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 sstride, u32 cand) {
-    // (a lane that passed both filters almost always matches, so there is no early exit; the
-    //  partial unroll keeps several independent L2 loads in flight)
+__device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u32 cstride, u32 cand) {
+    // (a lane that passed both filters almost always matches, so there is no early exit)
     u32 acc = ~cand;
 #pragma unroll 8
-    for (int i = 0; i < BSI_N; ++i) acc |= xs[i] ^ ck[(u64)i * sstride];
+    for (int i = 0; i < BSI_N; ++i) acc |= xs[i] ^ ck[i * cstride];
     return ~acc;
 }
 
 // detection record of the lanes in m: cycle length, checkpoint time and the matched state code
+// A match against a FINAL checkpoint (never overwritten) only notes the slot: the matched state
+// (= the checkpoint itself) and the previous checkpoint are extracted from the scratch at the end
+// of the word, when all threads of the warp do so together instead of one diverged thread now.
+#define BSI_DEFERRED 0x80000000u
 __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
-                                           u64 *y_s, u64 sstride, const u32 *prev_ck, u32 prev_t) {
+                                           u64 *y_s, u64 sstride, const u32 *prev_ck, u32 prev_t,
+                                           u32 slot, bool deferred) {
     u32 *c0_s = c_s + 32ull * sstride;
     u64 *z_s = y_s + (u64)BSI_KW * 32ull * sstride;
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
+        if (deferred) {
+            lam_s[l * sstride] = lam;
+            c_s[l * sstride] = c;
+            c0_s[l * sstride] = BSI_DEFERRED | slot;
+            continue;
+        }
         u64 code[BSI_KW];
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) code[k] = 0ull;
@@ -265,7 +277,7 @@ __device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c,
                 u64 z = 0ull;
 #pragma unroll 8
                 for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
-                    z |= (u64)((prev_ck[(u64)i * sstride] >> l) & 1u) << (i & 63);
+                    z |= (u64)((prev_ck[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
                 z_s[(k * 32 + l) * sstride] = z;
             }
         }
@@ -281,14 +293,13 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                                               BsiFound *found_q, u64 *retry_q, u32 *scratch,
                                               BsiCounters *ctr) {
     const u32 tid = threadIdx.x;
-    u32 *const f2_s = (u32 *)bsi_smem + tid;                          // [slot][BSI_F2][BLOCK]
+    u32 *const ck_s = (u32 *)bsi_smem + tid;                          // checkpoints [slot][node][BLOCK]
     const u64 sstride = (u64)gridDim.x * BSI_BLOCK;
     const u64 gtid = (u64)blockIdx.x * BSI_BLOCK + tid;
-    u32 *const my_scratch = scratch + gtid;
-    // detection records of this thread's 32 lanes (rarely written): after the 3 checkpoint slots
-    u32 *const lam_s = scratch + 3ull * BSI_N * sstride + gtid;       // [32][sstride]
+    // detection records of this thread's 32 lanes (rarely written), in global memory
+    u32 *const lam_s = scratch + gtid;                                // [32][sstride]
     u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride], then c0 [32]
-    u64 *const y_s = (u64 *)(scratch + (3ull * BSI_N + 96ull) * sstride) + gtid;   // y, z: [2][KW][32][sstride]
+    u64 *const y_s = (u64 *)(scratch + 96ull * sstride) + gtid;       // y, z: [2][KW][32][sstride]
     u64 dev_steps = 0, n_without = 0, ref_steps = 0;
 
     for (;;) {
@@ -301,6 +312,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         BSI_FOR_FILTER(BSI_DECL_K1)
         BSI_FOR_FILTER(BSI_DECL_K2)
         u32 valid = 0u, F = 0u, alive = 0u;
+        u32 st0 = 0, st1 = 0, st2 = 0;           // checkpoint time held by each slot
 
         if (active) {
             // ---- x_0 .. x_lp ----------------------------------------------------------------
@@ -327,30 +339,37 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 
             alive = valid;
             u32 j = 0, ci = 0, armed = 0;
-            u32 st0 = 0, st1 = 0, st2 = 0;       // checkpoint time held by each slot
 
             // Cold path, taken when some lane passes a register filter.  Stage 2 refines the
-            // candidate lanes against BSI_F2 more checkpoint words kept in shared memory (inline,
-            // a handful of LDS); only if a lane survives that too is the state dumped to local
-            // memory for the full compare against the scratch (rolled loops: the hot loop's
-            // register allocation only sees the state words, the filter words and a few scalars).
+            // candidate lanes against a dozen more words of the checkpoint in shared memory
+            // (inline, a handful of LDS); only if a lane survives that too is the state dumped to
+            // local memory for the full compare against the shared-memory checkpoint (rolled
+            // loops: the hot loop's register allocation only sees the state words, the filter
+            // words and a few scalars).
 #define BSI_FULL(XS, J, S, ST, ACC)                                                  \
     {                                                                                \
         u32 cand_ = ~(ACC) & alive;                                                  \
         if (cand_) {                                                                 \
-            u32 m_ = bsi_slow_match(XS, my_scratch + (u64)(S) * BSI_N * sstride, sstride, cand_); \
+            BSI_COUNT(1)                                                             \
+            u32 m_ = bsi_slow_match(XS, ck_s + (S) * BSI_N * BSI_BLOCK, BSI_BLOCK, cand_); \
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
                 bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s, sstride,       \
-                           (S) > 0 ? my_scratch + (u64)((S) - 1) * BSI_N * sstride : nullptr, \
-                           (S) == 1 ? st0 : st1);                                    \
+                           (S) > 0 ? ck_s + ((S) - 1) * BSI_N * BSI_BLOCK : nullptr,  \
+                           (S) == 1 ? st0 : st1, (S), (S) > 0 || (ST) >= sched.first_final); \
             }                                                                        \
         }                                                                            \
     }
+#if BSI_STATS
+#define BSI_COUNT(k) atomicAdd(&ctr->pad[k], 1ull);
+#else
+#define BSI_COUNT(k)
+#endif
 #define BSI_STAGE2(X, S, ACC)                                                        \
     if (ACC != 0xFFFFFFFFu) {                                                        \
-        const u32 *p2_ = f2_s + (S) * BSI_F2 * BSI_BLOCK;                             \
+        BSI_COUNT(0)                                                                 \
+        const u32 *p2_ = ck_s + (S) * BSI_N * BSI_BLOCK;                              \
         BSI_CMP_FILTER2_MEM(ACC, X, p2_, BSI_BLOCK)                                  \
     }
             // register filters of state X against the armed slots: p_s = lanes that CANNOT match
@@ -461,9 +480,8 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 // checkpoint due at time j: state a (already compared) goes into its slot
                 if (ci < sched.n_ck && sched.ck_time[ci] == j) {
                     const u32 s = sched.ck_slot[ci];
-                    u32 *p_ = my_scratch + (u64)s * BSI_N * sstride;
-                    BSI_STORE_ALL(a, p_, sstride)
-                    BSI_STORE_FILTER2(a, (f2_s + s * BSI_F2 * BSI_BLOCK), BSI_BLOCK)
+                    u32 *p_ = ck_s + s * BSI_N * BSI_BLOCK;
+                    BSI_STORE_ALL(a, p_, BSI_BLOCK)
                     if (s == 0u) { BSI_FOR_FILTER(BSI_SAVE_K0) st0 = j; }
                     else if (s == 1u) { BSI_FOR_FILTER(BSI_SAVE_K1) st1 = j; }
                     else { BSI_FOR_FILTER(BSI_SAVE_K2) st2 = j; }
@@ -506,6 +524,26 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 r.c = c_s[l * sstride];
                 r.c0 = c_s[(32 + l) * sstride];
                 r.pad = 0u;
+                if (r.c0 & BSI_DEFERRED) {
+                    // y = the matched final checkpoint, z = the final checkpoint before it
+                    const u32 slot = r.c0 & 3u;
+                    const u32 *py = ck_s + slot * BSI_N * BSI_BLOCK;
+                    const u32 *pz = py - BSI_N * BSI_BLOCK;
+                    r.c0 = slot == 0u ? 0u : (slot == 1u ? st0 : st1);
+#pragma unroll
+                    for (int k = 0; k < BSI_KW; ++k) {
+                        u64 y = 0ull, z = 0ull;
+#pragma unroll 8
+                        for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
+                            y |= (u64)((py[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
+                        if (slot) {
+#pragma unroll 8
+                            for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
+                                z |= (u64)((pz[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
+                        }
+                        r.y[k] = y; r.key[k] = y; r.z[k] = z;
+                    }
+                }
                 found_q[base_f++] = r;
             }
         }

@@ -117,7 +117,9 @@ typedef struct bsi_plan_opts {
     uint32_t keep_source;      /* unused: the generated source is always kept */
     uint32_t block_threads;    /* threads per block of the trajectory kernels; 0 = auto (64) */
     uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto       */
-    uint32_t reserved[9];
+    uint32_t debug_stats;      /* 1: count filter events (stats->reserved[0] = stage-2 filter entries,
+                                  [1] = full compares); costs atomics, for tuning only */
+    uint32_t reserved[8];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */

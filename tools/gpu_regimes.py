@@ -4,11 +4,11 @@ from math import inf
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from boolsi_b200 import _lib, synth
 n_free = int(sys.argv[1])
-for k, seed, max_t in [(2, 0, 1000), (2, 1, inf), (1, 0, inf), (3, 1, 1000), (3, 2, 1000)]:
+for k, seed, max_t in [(3, 0, 1000), (3, 2, 1000)] if len(sys.argv) > 2 else [(2, 0, 1000), (2, 1, inf), (1, 0, inf), (3, 1, 1000), (3, 2, 1000)]:
     cfg = synth.random_attract_problem(64, k, seed, n_free=n_free)
     pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
                             cfg['simulation problem variations'])
-    plan = _lib.Plan(pk, _lib.MODE_ATTRACT)
+    plan = _lib.Plan(pk, _lib.MODE_ATTRACT, **(eval(sys.argv[2]) if len(sys.argv) > 2 else {}))
     for rep in range(2):
         plan.table_clear()
         st = plan.attract_run(0, pk.n_problems, max_t, inf)
