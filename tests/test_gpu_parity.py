@@ -236,3 +236,31 @@ def test_full_size_headline_job_properties():
     with _lib.Plan(_lib.PackedProblem(*args2), _lib.MODE_ATTRACT) as plan:
         st2 = plan.attract_run(0, n, 1000, inf)
         assert _table_rows(plan) == whole and st2['steps'] == st['steps']
+
+
+def test_full_size_target_job_properties():
+    """BASELINE.json configs[4] shape at reduced count (2^24 of the 2^28 sampled initial states):
+    N=128, K=4, fixed nodes + per-step perturbations, max_t=500.  Hits come back in index order,
+    a sub-range run gives exactly the hits of that sub-range, and an oracle slice agrees."""
+    from oracle import coracle
+    cfg = synth.random_target_problem(128, 4, 0, n_free=24, n_target_nodes=6)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    pk = _lib.PackedProblem(*args)
+    tgt = _lib.make_target(cfg['target node set'], cfg['target substate code'], pk.kw)
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt) as plan:
+        hit_index, hit_t, st = plan.target_run(0, pk.n_problems, 500)
+        assert st['n_found'] == len(hit_index)
+        assert np.all(np.diff(hit_index.astype(np.int64)) > 0)                 # enumeration order
+        assert np.all(hit_t <= 500)
+        lo, hi = (1 << 23) + 77, (1 << 23) + 77 + 40000
+        sub_index, sub_t, _ = plan.target_run(lo, hi, 500)
+        sel = (hit_index >= lo) & (hit_index < hi)
+        assert np.array_equal(sub_index, hit_index[sel]) and np.array_equal(sub_t, hit_t[sel])
+        first5, _, st5 = plan.target_run(0, pk.n_problems, 500, 5)
+        assert np.array_equal(first5, hit_index[:5]) and st5['n_found'] == st['n_found']
+    sp = coracle.Space(*args)
+    rec = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 500, lo, lo + 4096)
+    want = np.nonzero(rec['reached'])[0] + lo
+    got = hit_index[(hit_index >= lo) & (hit_index < lo + 4096)]
+    assert np.array_equal(got.astype(np.int64), want.astype(np.int64))
