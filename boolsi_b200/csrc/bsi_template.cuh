@@ -19,12 +19,13 @@
 //       c_(i-1) < mu <= c_i and mu + lambda <= H is matched by time c_i + lambda < H + gap, so
 //       running to H + max gap - 1 PROVES "mu + lambda > H" for every lane still unmatched.
 //       The per-step compare is a FILTER over a few nodes held in registers; only when some lane
-//       passes the filter is the full state compared against the checkpoint kept in an
-//       L2-resident scratch (persistent grid: scratch is sized by resident threads).
+//       passes the filter (and a second filter over a dozen more words) is the full state
+//       compared against the checkpoint, which is kept in shared memory.
 //   bsi_resolve_key    canonical key = minimum state code over the cycle (model.py:140-149,
 //       attract.py:296) by a bit-sliced lexicographic-minimum walk of the cycle.
-//   bsi_resolve_mu     exact mu by walking x_j (from the problem index) in lock-step with the
-//       periodic extension of the cycle; then acceptance (mu + lambda <= T, lambda <=
+//   bsi_resolve_mu     exact mu by walking x_j (from the previous checkpoint, whose time is
+//       provably < mu, or from the problem index) in lock-step with the periodic extension of
+//       the cycle; then acceptance (mu + lambda <= T, lambda <=
 //       max_attractor_l, attract.py:294) and aggregation into the device attractor table.
 
 typedef unsigned char u8;
