@@ -130,7 +130,8 @@ __device__ __noinline__ void bsi_table_add(BsiSlot *table, u32 log2_slots, const
                                            u64 s1, u64 s2, u32 lam, BsiCounters *ctr) {
     const u64 mask = ((u64)1 << log2_slots) - 1;
     u64 pos = bsi_hash_key(key) & mask;
-    for (u64 probe = 0; probe <= mask; ++probe, pos = (pos + 1) & mask) {
+    // (a bounded probe sequence: a table this full is reported as overflow, not searched on)
+    for (u64 probe = 0; probe <= mask && probe < 4096; ++probe, pos = (pos + 1) & mask) {
         BsiSlot *s = table + pos;
         u32 f = *((volatile u32 *)&s->flag);
         if (f == 0u) {

@@ -264,3 +264,18 @@ def test_full_size_target_job_properties():
     want = np.nonzero(rec['reached'])[0] + lo
     got = hit_index[(hit_index >= lo) & (hit_index < lo + 4096)]
     assert np.array_equal(got.astype(np.int64), want.astype(np.int64))
+
+
+def test_attractor_table_overflow_is_reported():
+    """More attractors than table slots: BSI_E_CAPACITY, not a hang or a silent drop."""
+    n = 14
+    preds = [[i] for i in range(n)]                         # identity network: every state is a fixed point
+    tts = [{(False,): False, (True,): True} for _ in range(n)]
+    pk = _lib.PackedProblem(preds, tts, ([False] * n, {}, {}), (list(range(n)), [], []))
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, table_log2_slots=10) as plan:
+        with pytest.raises(_lib.BsiError) as e:
+            plan.attract_run(0, 1 << n, inf, inf)
+        assert e.value.status == -4
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, table_log2_slots=16) as plan:
+        st = plan.attract_run(0, 1 << n, inf, inf)
+        assert plan.table_count() == 1 << n and st['n_found'] == 1 << n and st['steps'] == 1 << n
