@@ -18,6 +18,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <random>
 #include <string>
@@ -179,12 +180,12 @@ struct bsi_plan {
     bsi::GenInfo info;
     bsi_plan_opts opts{};
     std::string source, log;
-    std::vector<char> cubin;
+    std::vector<char> cubins[5];     // per BSI_UNIT (1 dense, 2 queue, 3 resolve, 4 the rest)
     int block = 64;
     int device = -1;           // -1: compile-only plan
     CUdevice dev = 0;
     CUcontext ctx = nullptr;
-    CUmodule mod = nullptr;
+    CUmodule mods[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     CUstream own_stream = nullptr, stream = nullptr;
     CUfunction f_dense = nullptr, f_queue = nullptr, f_key = nullptr, f_mu = nullptr,
                f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
@@ -337,6 +338,66 @@ std::vector<int> choose_filter(const bsi::Model &m, int want, std::vector<int> *
     return f;
 }
 
+struct UnitResult {
+    int status = BSI_OK;
+    std::string error, log;
+    std::vector<char> cubin;
+};
+
+// One NVRTC program -> sm_100a cubin, with an in-process cache keyed by the source text (the
+// same network + space + mode specialises to the same source).
+UnitResult compile_unit(std::string src) {
+    static std::mutex cache_mu;
+    static std::map<std::string, std::pair<std::vector<char>, std::string>> cache;
+    UnitResult out;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        auto it = cache.find(src);
+        if (it != cache.end()) {
+            out.cubin = it->second.first;
+            out.log = it->second.second;
+            return out;
+        }
+    }
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "bsi_kernels.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) {
+        out.status = BSI_E_NVRTC;
+        out.error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
+        return out;
+    }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+    r = nvrtcCompileProgram(prog, 4, opts);
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    out.log.assign(log_size ? log_size : 1, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, &out.log[0]);
+    while (!out.log.empty() && out.log.back() == '\0') out.log.pop_back();
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        out.status = BSI_E_NVRTC;
+        out.error = std::string("kernel specialisation failed (") + nvrtcGetErrorString(r) + "):\n" + out.log.substr(0, 3500);
+        return out;
+    }
+    size_t cubin_size = 0;
+    r = nvrtcGetCUBINSize(prog, &cubin_size);
+    if (r != NVRTC_SUCCESS || cubin_size == 0) {
+        nvrtcDestroyProgram(&prog);
+        out.status = BSI_E_NVRTC;
+        out.error = std::string("nvrtcGetCUBINSize: ") + nvrtcGetErrorString(r);
+        return out;
+    }
+    out.cubin.resize(cubin_size);
+    nvrtcGetCUBIN(prog, out.cubin.data());
+    nvrtcDestroyProgram(&prog);
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (cache.size() >= 256) cache.clear();
+        cache[src] = {out.cubin, out.log};
+    }
+    return out;
+}
+
 int compile_plan(bsi_plan *p) {
     StageTimer tm;
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
@@ -353,48 +414,26 @@ int compile_plan(bsi_plan *p) {
     p->source += bsi_template_src;
     tm.lap("generate source");
 
-    // in-process cache: the same network + space + mode specialises to the same source
-    static std::mutex cache_mu;
-    static std::map<std::string, std::pair<std::vector<char>, std::string>> cache;
-    {
-        std::lock_guard<std::mutex> lk(cache_mu);
-        auto it = cache.find(p->source);
-        if (it != cache.end()) {
-            p->cubin = it->second.first;
-            p->log = it->second.second;
-            return BSI_OK;
-        }
+    // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
+    // thread-safe across programs): the two trajectory kernels dominate the compile time.
+    std::vector<int> units;
+    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 4}; else units = {4};
+    std::vector<std::future<UnitResult>> jobs;
+    for (int u : units) {
+        std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
+        jobs.push_back(std::async(std::launch::async, compile_unit, std::move(src)));
     }
-
-    nvrtcProgram prog;
-    nvrtcResult r = nvrtcCreateProgram(&prog, p->source.c_str(), "bsi_kernels.cu", 0, nullptr, nullptr);
-    if (r != NVRTC_SUCCESS) return fail(BSI_E_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
-    r = nvrtcCompileProgram(prog, 4, opts);
-    size_t log_size = 0;
-    nvrtcGetProgramLogSize(prog, &log_size);
-    p->log.assign(log_size ? log_size : 1, '\0');
-    if (log_size) nvrtcGetProgramLog(prog, &p->log[0]);
-    while (!p->log.empty() && p->log.back() == '\0') p->log.pop_back();
-    if (r != NVRTC_SUCCESS) {
-        nvrtcDestroyProgram(&prog);
-        return fail(BSI_E_NVRTC, "kernel specialisation failed (%s):\n%.3500s", nvrtcGetErrorString(r), p->log.c_str());
+    int rc = BSI_OK;
+    p->log.clear();
+    for (size_t i = 0; i < units.size(); ++i) {
+        UnitResult r = jobs[i].get();
+        if (r.status != BSI_OK && rc == BSI_OK) { rc = r.status; g_err = r.error; }
+        if (!r.log.empty()) p->log += r.log + "\n";
+        p->cubins[units[i]] = std::move(r.cubin);
     }
-    size_t cubin_size = 0;
-    r = nvrtcGetCUBINSize(prog, &cubin_size);
-    if (r != NVRTC_SUCCESS || cubin_size == 0) {
-        nvrtcDestroyProgram(&prog);
-        return fail(BSI_E_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
-    }
-    p->cubin.resize(cubin_size);
-    nvrtcGetCUBIN(prog, p->cubin.data());
-    nvrtcDestroyProgram(&prog);
-    {
-        std::lock_guard<std::mutex> lk(cache_mu);
-        if (cache.size() >= 64) cache.clear();
-        cache[p->source] = {p->cubin, p->log};
-    }
-    return BSI_OK;
+    tm.lap("nvrtc (parallel units)");
+    p->source = "#define BSI_UNIT 0\n" + p->source;       // what bsi_plan_source shows: the whole TU
+    return rc;
 }
 
 int load_plan(bsi_plan *p, int device) {
@@ -412,18 +451,19 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
     if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
     CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
-    CU_CHECK(cuModuleLoadData(&p->mod, p->cubin.data()));
+    for (int u = 1; u <= 4; ++u)
+        if (!p->cubins[u].empty()) CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u].data()));
     tm.lap("cuModuleLoadData");
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
     p->stream = p->own_stream;
-    CU_CHECK(cuModuleGetFunction(&p->f_traj, p->mod, "bsi_trajectories"));
+    CU_CHECK(cuModuleGetFunction(&p->f_traj, p->mods[4], "bsi_trajectories"));
     if (p->m.mode == BSI_MODE_ATTRACT) {
-        CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mod, "bsi_attract_dense"));
-        CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mod, "bsi_attract_queue"));
-        CU_CHECK(cuModuleGetFunction(&p->f_key, p->mod, "bsi_resolve_key"));
-        CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mod, "bsi_resolve_mu"));
-        CU_CHECK(cuModuleGetFunction(&p->f_export, p->mod, "bsi_table_export"));
-        CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mod, "bsi_table_merge"));
+        CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mods[1], "bsi_attract_dense"));
+        CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
+        CU_CHECK(cuModuleGetFunction(&p->f_key, p->mods[3], "bsi_resolve_key"));
+        CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
+        CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
+        CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
         p->main_smem = (size_t)3 * p->m.n * p->block * 4;      // the three checkpoint slots
         if (p->main_smem > 48 * 1024) {
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
@@ -444,7 +484,7 @@ int load_plan(bsi_plan *p, int device) {
         if (rc) return rc;
         CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
     }
-    if (p->m.mode == BSI_MODE_TARGET) CU_CHECK(cuModuleGetFunction(&p->f_target, p->mod, "bsi_target_main"));
+    if (p->m.mode == BSI_MODE_TARGET) CU_CHECK(cuModuleGetFunction(&p->f_target, p->mods[4], "bsi_target_main"));
     int rc = ensure(p, p->ctr, sizeof(Counters));
     if (rc) return rc;
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
@@ -480,7 +520,7 @@ int create_plan(const bsi_network_desc *network, const bsi_space_desc *space, in
 
 int need_device(bsi_plan *p, int mode) {
     if (!p) return fail(BSI_E_ARG, "null plan");
-    if (p->device < 0 || !p->mod) return fail(BSI_E_CUDA, "this plan was specialised without a device and cannot run (no CPU fallback)");
+    if (p->device < 0 || !p->mods[4]) return fail(BSI_E_CUDA, "this plan was specialised without a device and cannot run (no CPU fallback)");
     if (mode >= 0 && p->m.mode != mode) return fail(BSI_E_ARG, "plan was created for another mode");
     return BSI_OK;
 }
@@ -544,7 +584,7 @@ void bsi_plan_destroy(bsi_plan *p) {
             tm.lap("destroy: buffers");
             for (CUevent e : p->events) cu().p_cuEventDestroy(e);
             if (p->own_stream) cu().p_cuStreamDestroy(p->own_stream);
-            if (p->mod) cu().p_cuModuleUnload(p->mod);
+            for (CUmodule m : p->mods) if (m) cu().p_cuModuleUnload(m);
             tm.lap("destroy: module/stream");
         }
     }
@@ -593,8 +633,9 @@ const char *bsi_plan_build_log(const bsi_plan *p) { return p ? p->log.c_str() : 
 
 int bsi_plan_cubin(const bsi_plan *p, const void **data, uint64_t *bytes) {
     if (!p || !data || !bytes) return fail(BSI_E_ARG, "null pointer");
-    *data = p->cubin.data();
-    *bytes = p->cubin.size();
+    const std::vector<char> &c = p->cubins[p->m.mode == BSI_MODE_ATTRACT ? 1 : 4];
+    *data = c.data();
+    *bytes = c.size();
     return BSI_OK;
 }
 
@@ -626,7 +667,7 @@ int bsi_compile_only(const bsi_network_desc *network, const bsi_space_desc *spac
         snprintf(log, (size_t)log_cap, "%s", src.c_str());
     }
     if (rc == BSI_OK) {
-        if (cubin_bytes) *cubin_bytes = p->cubin.size();
+        if (cubin_bytes) { *cubin_bytes = 0; for (auto &c : p->cubins) *cubin_bytes += c.size(); }
         bsi_plan_destroy(p);
     }
     return rc;
@@ -1040,7 +1081,7 @@ int bsi_measure_update_rate(bsi_plan *p, double *word_steps_per_s, double *lop3_
     if (rc) return rc;
     CtxGuard g(p);
     CUfunction f = nullptr;
-    CU_CHECK(cuModuleGetFunction(&f, p->mod, "bsi_update_rate"));
+    CU_CHECK(cuModuleGetFunction(&f, p->mods[4], "bsi_update_rate"));
     if ((rc = ensure(p, p->misc, 256))) return rc;
     int per_sm = 0;
     CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, p->block, 0));

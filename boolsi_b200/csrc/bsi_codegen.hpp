@@ -563,7 +563,7 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         }
         o << "}\n";
     }
-    // code words <-> bit-sliced words
+    // code words <-> bit-sliced words, one lane at a time (rare paths)
     {
         o << "#define BSI_INSERT(X, l, c) {";
         for (int i = 0; i < n; ++i)
@@ -572,6 +572,29 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         for (int w = 0; w < m.kw; ++w) o << " c[" << w << "] = 0ull;";
         for (int i = 0; i < n; ++i)
             o << " c[" << (i >> 6) << "] |= (unsigned long long)((X##" << i << " >> (l)) & 1u) << " << (i & 63) << ";";
+        o << " }\n";
+    }
+    // ... and all 32 lanes at once through 32x32 bit-matrix transposes (bsi_transpose32 maps
+    // B[r] bit c = A[31-c] bit 31-r, hence the reversed indices): CW is u64 [32 lanes][KW].
+    {
+        const int blocks = (n + 31) / 32;
+        o << "#define BSI_PACK(X, CW) { unsigned int A_[32];";
+        for (int b = 0; b < blocks; ++b) {
+            o << " _Pragma(\"unroll\") for (int k_ = 0; k_ < 32; ++k_) A_[k_] = (unsigned int)((CW)[31 - k_]["
+              << (b >> 1) << "] >> " << (32 * (b & 1)) << "); bsi_transpose32(A_);";
+            for (int i = 0; i < 32 && 32 * b + i < n; ++i)
+                o << " X##" << (32 * b + i) << " = A_[" << (31 - i) << "];";
+        }
+        o << " }\n#define BSI_UNPACK(CW, X) { unsigned int A_[32];";
+        for (int b = 0; b < blocks; ++b) {
+            for (int k = 0; k < 32; ++k) {
+                int node = 32 * b + 31 - k;
+                if (node < n) o << " A_[" << k << "] = X##" << node << ";";
+                else o << " A_[" << k << "] = 0u;";
+            }
+            o << " bsi_transpose32(A_); _Pragma(\"unroll\") for (int k_ = 0; k_ < 32; ++k_) (CW)[31 - k_]["
+              << (b >> 1) << "] " << ((b & 1) ? "|= (unsigned long long)A_[k_] << 32;" : "= (unsigned long long)A_[k_];");
+        }
         o << " }\n";
     }
     return o.str();

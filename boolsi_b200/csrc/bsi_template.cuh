@@ -41,6 +41,22 @@ __device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
 
 #define BSI_MAX_CK 72
 
+// 32x32 bit-matrix transpose in place (Hacker's Delight 7-3): B[r] bit c = A[31-c] bit 31-r.
+// Turns 32 node words (bit = lane) into 32 lane words (bit = node) and back in 5 x 16 butterfly
+// steps instead of 32 x 32 single-bit moves (BSI_PACK / BSI_UNPACK in the generated header).
+__device__ __forceinline__ void bsi_transpose32(unsigned int (&A)[32]) {
+    unsigned int m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const unsigned int t = (A[k] ^ (A[k + j] >> j)) & m;
+            A[k] ^= t;
+            A[k + j] ^= (t << j);
+        }
+    }
+}
+
 struct BsiCounters {
     // reset before every round
     u64 next_word;      // work counter of the persistent trajectory kernel
@@ -323,18 +339,23 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 valid = bsi_valid_mask(W, idx_begin, idx_end);
                 BSI_INIT_DENSE(a, W)
             } else {
-                BSI_FOR_NODES(BSI_ZERO_A)
+                u64 cw_[32][BSI_KW];
+#pragma unroll 1
                 for (u32 l = 0; l < 32; ++l) {
                     u64 q = (w << 5) + l;
+                    u64 c_[BSI_KW];
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) c_[i] = 0ull;
                     if (q < n_in) {
-                        u64 c_[BSI_KW];
                         u64 lp_lane_ = 0;
                         BSI_LANE_SETUP(l, in_queue[q], c_)
                         (void)lp_lane_;
-                        BSI_INSERT(a, l, c_)
                         valid |= 1u << l;
                     }
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = c_[i];
                 }
+                BSI_PACK(a, cw_)
             }
             BSI_PREFIX(BSI_LP_ORIGIN)
             BSI_FOR_FILTER(BSI_ZERO_K)
@@ -567,6 +588,10 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     if (ref_steps) atomicAdd(&ctr->steps, ref_steps);
 }
 
+// The translation unit is compiled once per BSI_UNIT (in parallel, see bsi.cpp): 1 = dense
+// trajectory kernel, 2 = queue trajectory kernel, 3 = resolution kernels, 4 = everything else;
+// 0 = all of it (the ahead-of-time nvcc build check).
+#if BSI_UNIT == 0 || BSI_UNIT == 1
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
 bsi_attract_dense(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end, const BsiSched sched,
                   int final_round, u64 stop_t, BsiFound *found_q, u64 *retry_q, u32 *scratch,
@@ -574,17 +599,21 @@ bsi_attract_dense(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end, const BsiS
     bsi_main_body<true>(word0, n_words, idx_begin, idx_end, nullptr, 0, sched, final_round, stop_t,
                         found_q, retry_q, scratch, ctr);
 }
+#endif
 
+#if BSI_UNIT == 0 || BSI_UNIT == 2
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
 bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final_round, u64 stop_t,
                   BsiFound *found_q, u64 *retry_q, u32 *scratch, BsiCounters *ctr) {
     bsi_main_body<false>(0, (n_in + 31) >> 5, 0, 0, in_queue, n_in, sched, final_round, stop_t,
                          found_q, retry_q, scratch, ctr);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // attract: exact resolution of the matched lanes
 // ---------------------------------------------------------------------------------------------
+#if BSI_UNIT == 0 || BSI_UNIT == 3
 
 // Canonical key = lexicographic minimum over the cycle with node N-1 most significant, i.e. the
 // minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
@@ -601,20 +630,21 @@ bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
-        BSI_FOR_NODES(BSI_ZERO_A)
         u32 valid = 0u, lam_max = 0u;
+        u64 cw_[32][BSI_KW];
+#pragma unroll 1
         for (u32 l = 0; l < 32; ++l) {
             u64 q = (w << 5) + l;
-            if (q < n_found) {
-                u64 c_[BSI_KW];
+            const bool in = q < n_found;
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].y[i];
-                BSI_INSERT(a, l, c_)
+            for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = in ? found_q[q].y[i] : 0ull;
+            if (in) {
                 valid |= 1u << l;
                 lam_max = max(lam_max, found_q[q].lam);
             }
         }
         if (lam_max <= 1u) continue;
+        BSI_PACK(a, cw_)
         BSI_FOR_NODES(BSI_COPY_CA)
         // lt_: lanes where X < c (decided at the most significant differing node)
 #define BSI_LEX_NODE(i)                                                           \
@@ -641,12 +671,12 @@ bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
 #undef BSI_LEX_STEP
 #undef BSI_SEL_NODE
 #undef BSI_LEX_NODE
+        BSI_UNPACK(cw_, c)
+#pragma unroll 1
         for (u32 l = 0; l < 32; ++l) {
             if ((valid >> l) & 1u) {
-                u64 c_[BSI_KW];
-                BSI_EXTRACT(c, l, c_)
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) found_q[(w << 5) + l].key[i] = c_[i];
+                for (int i = 0; i < BSI_KW; ++i) found_q[(w << 5) + l].key[i] = cw_[l][i];
             }
         }
     }
@@ -673,15 +703,14 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
-        BSI_FOR_NODES(BSI_ZERO_B)
         u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u;
+        u64 cw_[32][BSI_KW];
+#pragma unroll 1
         for (u32 l = 0; l < 32; ++l) {
             u64 q = (w << 5) + l;
-            if (q < n_found) {
-                u64 c_[BSI_KW];
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].y[i];
-                BSI_INSERT(b, l, c_)
+            for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = q < n_found ? found_q[q].y[i] : 0ull;
+            if (q < n_found) {
                 valid |= 1u << l;
                 const u32 lam = found_q[q].lam, c = found_q[q].c, c0 = found_q[q].c0;
                 const u32 adv = (lam - (c - c0) % lam) % lam;
@@ -691,6 +720,7 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
                 if (c0 == 0u) from_idx |= 1u << l;
             }
         }
+        BSI_PACK(b, cw_)
         // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
 #define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
         {
@@ -699,6 +729,7 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
                 if (k == next_ev) {
                     go_ = 0u;
                     next_ev = 0xFFFFFFFFu;
+#pragma unroll 1
                     for (u32 l = 0; l < 32; ++l) {
                         if (!((valid >> l) & 1u)) continue;
                         u32 adv = aux_s[l * BSI_BLOCK + tid];
@@ -716,32 +747,41 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
 #define BSI_COPY_CB(i) c##i = b##i;
 #define BSI_COPY_BC(i) b##i = c##i;
 #define BSI_MASK_A(i) a##i &= from_idx;
+#define BSI_OR_AB(i) a##i |= b##i;
             BSI_FOR_NODES(BSI_COPY_CB)
             BSI_FOR_NODES(BSI_ZERO_A)
             if (from_idx) {
+#pragma unroll 1
                 for (u32 l = 0; l < 32; ++l) {
                     u64 q = (w << 5) + l;
+                    u64 c_[BSI_KW];
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) c_[i] = 0ull;
                     if ((from_idx >> l) & 1u) {
-                        u64 c_[BSI_KW];
                         u64 lp_lane_ = 0;
                         BSI_LANE_SETUP(l, found_q[q].idx, c_)
                         (void)lp_lane_;
-                        BSI_INSERT(a, l, c_)
                     }
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = c_[i];
                 }
+                BSI_PACK(a, cw_)
                 BSI_PREFIX(BSI_LP_ORIGIN)
                 BSI_FOR_NODES(BSI_MASK_A)
             }
-            for (u32 l = 0; l < 32; ++l) {
-                u64 q = (w << 5) + l;
-                if (((valid & ~from_idx) >> l) & 1u) {
-                    u64 c_[BSI_KW];
+            if (valid & ~from_idx) {
+#pragma unroll 1
+                for (u32 l = 0; l < 32; ++l) {
+                    u64 q = (w << 5) + l;
+                    const bool use_z = ((valid & ~from_idx) >> l) & 1u;
 #pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) c_[i] = found_q[q].z[i];
-                    BSI_INSERT(a, l, c_)
+                    for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = use_z ? found_q[q].z[i] : 0ull;
                 }
+                BSI_PACK(b, cw_)
+                BSI_FOR_NODES(BSI_OR_AB)
             }
             BSI_FOR_NODES(BSI_COPY_BC)
+#undef BSI_OR_AB
 #undef BSI_MASK_A
 #undef BSI_COPY_CB
 #undef BSI_COPY_BC
@@ -821,6 +861,9 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
 }
 
+#endif  // BSI_UNIT 3
+
+#if BSI_UNIT == 0 || BSI_UNIT == 4
 // ---- attractor table: export / merge ------------------------------------------------------------
 // Compacts the table into out[0 .. cap).  With `header` set, the last block to finish also writes
 // one header record there: key = {count, trajectory-steps, accepted, without}, n = 0 (so that a
@@ -874,8 +917,10 @@ extern "C" __global__ void bsi_table_merge(BsiSlot *table, u32 log2_slots, const
     }
 }
 
+#endif  // BSI_UNIT 4
 #endif  // BSI_MODE == 1
 
+#if BSI_UNIT == 0 || BSI_UNIT == 4
 // ---------------------------------------------------------------------------------------------
 // measurement: the bare update loop (no compare, no stores) of THIS network -- the practical
 // ceiling of the trajectory kernels, to set beside the ideal-chain lop3 peak
@@ -913,14 +958,17 @@ bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lane
     if ((w << 5) >= n_lanes) return;
     BSI_FOR_NODES(BSI_DECL_A)
     BSI_FOR_NODES(BSI_DECL_B)
-    BSI_FOR_NODES(BSI_ZERO_A)
     BSI_FOR_FIXVAR(BSI_DECL_FIXVAR)
     BSI_FOR_PVAR(BSI_DECL_PVAR)
     u32 valid = 0u;
+    u64 cw_[32][BSI_KW];
+#pragma unroll 1
     for (u32 l = 0; l < 32; ++l) {
         u64 q = (w << 5) + l;
+        u64 c_[BSI_KW];
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) c_[i] = 0ull;
         if (q < n_lanes) {
-            u64 c_[BSI_KW];
             u64 lp_lane_ = 0;
             // (the setup also fills the per-lane fixed-node masks; with explicit codes the index
             //  is irrelevant for them because orbits are only asked for in attract mode)
@@ -930,18 +978,23 @@ bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lane
 #pragma unroll
                 for (int i = 0; i < BSI_KW; ++i) c_[i] = codes[q * BSI_KW + i];
             }
-            BSI_INSERT(a, l, c_)
             valid |= 1u << l;
         }
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = c_[i];
     }
+    BSI_PACK(a, cw_)
     const bool perturbing = codes == nullptr;
+    // every state of all 32 lanes goes out as code words: one transpose per 32 nodes, then
+    // KW 64-bit stores per lane
 #define BSI_STORE(X, T)                                                           \
-    for (u32 l = 0; l < 32; ++l) {                                                \
-        if ((valid >> l) & 1u) {                                                  \
-            u64 c_[BSI_KW];                                                       \
-            BSI_EXTRACT(X, l, c_)                                                 \
-            u64 *dst = out + (((w << 5) + l) * (n_steps + 1) + (T)) * BSI_KW;     \
-            for (int i = 0; i < BSI_KW; ++i) dst[i] = c_[i];                      \
+    {                                                                             \
+        BSI_UNPACK(cw_, X)                                                        \
+        _Pragma("unroll 1") for (u32 l = 0; l < 32; ++l) {                        \
+            if ((valid >> l) & 1u) {                                              \
+                u64 *dst = out + (((w << 5) + l) * (n_steps + 1) + (T)) * BSI_KW; \
+                _Pragma("unroll") for (int i = 0; i < BSI_KW; ++i) dst[i] = cw_[l][i]; \
+            }                                                                     \
         }                                                                         \
     }
     BSI_STORE(a, 0)
@@ -982,25 +1035,33 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
 
     for (int pass = 0; pass < 2; ++pass) {
         // pass 0: hits and c = x_T;  pass 1 (only if needed): closure test against c
-        BSI_FOR_NODES(BSI_ZERO_A)
         valid = 0u;
-        for (u32 l = 0; l < 32; ++l) {
-            u64 q = (w << 5) + l;
-            if (q < n_lanes) {
+        {
+            u64 cw_[32][BSI_KW];
+#pragma unroll 1
+            for (u32 l = 0; l < 32; ++l) {
+                u64 q = (w << 5) + l;
                 u64 c_[BSI_KW];
-                u64 lp_lane_ = BSI_LP_ORIGIN;
-                // (re-running the setup in pass 1 is harmless: it only ORs the same mask bits)
-                BSI_LANE_SETUP(l, (in_queue ? in_queue[q] : idx_begin + q), c_)
-                lp_s[l * BSI_BLOCK + threadIdx.x] = (u32)lp_lane_;
-                BSI_INSERT(a, l, c_)
-                valid |= 1u << l;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) c_[i] = 0ull;
+                if (q < n_lanes) {
+                    u64 lp_lane_ = BSI_LP_ORIGIN;
+                    // (re-running the setup in pass 1 is harmless: it only ORs the same mask bits)
+                    BSI_LANE_SETUP(l, (in_queue ? in_queue[q] : idx_begin + q), c_)
+                    lp_s[l * BSI_BLOCK + threadIdx.x] = (u32)lp_lane_;
+                    valid |= 1u << l;
+                }
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = c_[i];
             }
+            BSI_PACK(a, cw_)
         }
         u32 started = 0u;
         u32 alive = valid & ~hit;
         for (u64 t = 0;; ++t) {
             // lanes whose perturbations are all carried out by time t
             if (t <= BSI_LP_MAX) {
+#pragma unroll 1
                 for (u32 l = 0; l < 32; ++l)
                     if (((valid >> l) & 1u) && lp_s[l * BSI_BLOCK + threadIdx.x] == (u32)t) started |= 1u << l;
             }
@@ -1043,6 +1104,7 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
     }
 
     u64 steps = 0;
+#pragma unroll 1
     for (u32 l = 0; l < 32; ++l) {
         if (!((valid >> l) & 1u)) continue;
         u64 q = (w << 5) + l;
@@ -1067,3 +1129,4 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
     if (dev_steps) atomicAdd(&ctr->device_steps, dev_steps);
 }
 #endif  // BSI_MODE == 2
+#endif  // BSI_UNIT 4

@@ -172,7 +172,8 @@ int bsi_plan_set_stream(bsi_plan *plan, void *cuda_stream);   /* cudaStream_t; N
 /* Generated CUDA source / build log (NUL-terminated, owned by the plan). */
 const char *bsi_plan_source(const bsi_plan *plan);
 const char *bsi_plan_build_log(const bsi_plan *plan);
-/* The sm_100a cubin NVRTC produced (owned by the plan). */
+/* The sm_100a cubin NVRTC produced for the plan's dominant kernel unit (owned by the plan):
+ * the dense attract trajectory kernel, or the trajectory/target unit in the other modes. */
 int bsi_plan_cubin(const bsi_plan *plan, const void **data, uint64_t *bytes);
 /* Persistent-grid geometry of the attract trajectory kernel on the plan's device. */
 int bsi_plan_launch_config(const bsi_plan *plan, uint32_t *n_sms, uint32_t *block_threads,
