@@ -180,14 +180,15 @@ struct bsi_plan {
     bsi::GenInfo info;
     bsi_plan_opts opts{};
     std::string source, log;
-    std::vector<char> cubins[5];     // per BSI_UNIT (1 dense, 2 queue, 3 resolve, 4 the rest)
+    std::vector<char> cubins[6];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 resolve, 4 the rest)
     int block = 64;
     int device = -1;           // -1: compile-only plan
     CUdevice dev = 0;
     CUcontext ctx = nullptr;
-    CUmodule mods[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    CUmodule mods[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CUstream own_stream = nullptr, stream = nullptr;
     CUfunction f_dense = nullptr, f_queue = nullptr, f_key = nullptr, f_mu = nullptr,
+               f_resolve = nullptr, f_finish = nullptr,
                f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
     int n_sms = 0;
     int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
@@ -417,7 +418,7 @@ int compile_plan(bsi_plan *p) {
     // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
     // thread-safe across programs): the two trajectory kernels dominate the compile time.
     std::vector<int> units;
-    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 4}; else units = {4};
+    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 5, 4}; else units = {4};
     std::vector<std::future<UnitResult>> jobs;
     for (int u : units) {
         std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
@@ -451,7 +452,7 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
     if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
     CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
-    for (int u = 1; u <= 4; ++u)
+    for (int u = 1; u <= 5; ++u)
         if (!p->cubins[u].empty()) CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u].data()));
     tm.lap("cuModuleLoadData");
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
@@ -461,7 +462,9 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mods[1], "bsi_attract_dense"));
         CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
         CU_CHECK(cuModuleGetFunction(&p->f_key, p->mods[3], "bsi_resolve_key"));
+        CU_CHECK(cuModuleGetFunction(&p->f_resolve, p->mods[5], "bsi_resolve"));
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
+        CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
         p->main_smem = (size_t)3 * p->m.n * p->block * 4;      // the three checkpoint slots
@@ -754,14 +757,19 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
             CU_CHECK(cuEventRecord(r0, p->stream));
             {
                 CUdeviceptr n_found_p = p->ctr.p + offsetof(Counters, n_found);
-                void *args_k[] = {&p->found_q.p, &n_found_p, &p->ctr.p};
-                unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
-                if ((rc = launch(p, p->f_key, grid_k, p->block, 0, args_k))) return rc;
+                // all four resolution kernels are launched; the device picks the pair that fits the
+                // queue length (see bsi_template.cuh), the other two return at once
+                uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
                 uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
-                void *args_m[] = {&p->found_q.p, &n_found_p, &t_rel, &cap_l, &stop_cap, &p->table.p,
+                void *args_k[] = {&p->found_q.p, &n_found_p, &few, &p->ctr.p};
+                void *args_m[] = {&p->found_q.p, &n_found_p, &few, &t_rel, &cap_l, &stop_cap, &p->table.p,
                                   &p->table_log2, &p->ctr.p};
+                unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
+                if ((rc = launch(p, p->f_key, grid_k, p->block, 0, args_k))) return rc;
                 if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
+                if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_k))) return rc;
+                if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;
             }
             CU_CHECK(cuEventRecord(r1, p->stream));
             tm.resolve.push_back({r0, r1});

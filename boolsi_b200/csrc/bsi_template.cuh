@@ -590,7 +590,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 
 // The translation unit is compiled once per BSI_UNIT (in parallel, see bsi.cpp): 1 = dense
 // trajectory kernel, 2 = queue trajectory kernel, 3 = resolution kernels, 4 = everything else;
-// 0 = all of it (the ahead-of-time nvcc build check).
+// 5 = the latency-oriented resolution kernels; 0 = all of it (the ahead-of-time nvcc build check).
 #if BSI_UNIT == 0 || BSI_UNIT == 1
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
 bsi_attract_dense(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end, const BsiSched sched,
@@ -613,20 +613,14 @@ bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final
 // ---------------------------------------------------------------------------------------------
 // attract: exact resolution of the matched lanes
 // ---------------------------------------------------------------------------------------------
-#if BSI_UNIT == 0 || BSI_UNIT == 3
+#if BSI_UNIT == 0 || BSI_UNIT == 3 || BSI_UNIT == 5
 
 // Canonical key = lexicographic minimum over the cycle with node N-1 most significant, i.e. the
 // minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
 // the cycle of found_q[32w + l] from y; walking more than lambda steps only revisits cycle
 // states, so all lanes of a word share the step count max lambda - 1.  lambda == 1: key = y.
-extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
-    const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    for (;;) {
-        const u64 w = bsi_grab_word(&ctr->next_word2);
-        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w >= n_words) continue;
+__device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64 w) {
+    {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
@@ -643,7 +637,7 @@ bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
                 lam_max = max(lam_max, found_q[q].lam);
             }
         }
-        if (lam_max <= 1u) continue;
+        if (lam_max <= 1u) return;
         BSI_PACK(a, cw_)
         BSI_FOR_NODES(BSI_COPY_CA)
         // lt_: lanes where X < c (decided at the most significant differing node)
@@ -688,18 +682,11 @@ bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, BsiCounters *ctr) {
 // a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
 // walks P(j); three register sets rotate so that no step needs a copy.
 // Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
-extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_attractor_l,
-               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
-    __shared__ u32 aux_s[32 * BSI_BLOCK];
+template <bool WRITE_PAD>
+__device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
+                                            BsiCounters *ctr) {
     const u32 tid = threadIdx.x;
-    const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    u64 steps = 0, n_acc = 0, n_rej = 0;
-    for (;;) {
-        const u64 w = bsi_grab_word(&ctr->next_word3);
-        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w >= n_words) continue;
+    {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
@@ -818,9 +805,28 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
         }
 #undef BSI_LOCK
         if (alive) atomicExch(&ctr->internal_error, 1ull);
+        // mu - c0 stays in aux_s; for bsi_resolve_finish (another kernel) mu goes into the record
+        if (WRITE_PAD) {
+#pragma unroll 1
+            for (u32 l = 0; l < 32; ++l)
+                if ((valid >> l) & 1u) found_q[(w << 5) + l].pad = found_q[(w << 5) + l].c0 + aux_s[l * BSI_BLOCK + tid];
+        }
 
+    }
+}
+
+// Acceptance (mu + lambda <= T, lambda <= max_attractor_l; reference attract.py:287-300) and
+// aggregation into the attractor table (attract.py:374-402) of the 32 lanes of word w; lanes of
+// one thread with equal keys are added once.
+template <bool FROM_AUX>
+__device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_found, u64 w, u64 T,
+                                                u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
+                                                u32 log2_slots, BsiCounters *ctr, u64 &steps,
+                                                u64 &n_acc, u64 &n_rej, const u32 *aux_s) {
+    {
+        const u64 left = n_found - (w << 5);
+        u32 todo = left >= 32 ? 0xFFFFFFFFu : ((1u << (u32)left) - 1u);
         // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
-        u32 todo = valid & ~alive;
         while (todo) {
             const u32 l0 = __ffs(todo) - 1;
             const BsiFound r0 = found_q[(w << 5) + l0];
@@ -835,7 +841,7 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
                 for (int i = 0; i < BSI_KW; ++i) same = same && (r->key[i] == r0.key[i]);
                 if (!same) continue;
                 todo &= ~(1u << l);
-                const u64 mu = (u64)r->c0 + aux_s[l * BSI_BLOCK + tid];
+                const u64 mu = FROM_AUX ? (u64)r->c0 + aux_s[l * BSI_BLOCK + threadIdx.x] : (u64)r->pad;
                 const u64 lam = r->lam;
                 if (mu + lam <= T) {                     // the loop stops at t = mu + lambda (model.py:201)
                     steps += BSI_LP_ORIGIN + mu + lam;
@@ -856,12 +862,92 @@ bsi_resolve_mu(const BsiFound *found_q, const u64 *n_found_p, u64 T, u64 max_att
             }
         }
     }
+}
+
+// Two ways to run the resolution, chosen ON THE DEVICE from the queue length (the host launches
+// all four kernels; the two that do not apply return at once):
+//  * many matched lanes (> few_words words): throughput matters -- bsi_resolve_key, then
+//    bsi_resolve_mu, which also finishes its lanes;
+//  * few matched lanes: the walks are latency-bound chains that form the tail after every
+//    trajectory kernel -- bsi_resolve runs the mu walks and the key walks side by side (first
+//    and second half of its task range; tasks are handed out 32 at a time, so a warp is never
+//    split between the two), then bsi_resolve_finish aggregates.
+#if BSI_UNIT != 5
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    if (n_words <= few_words) return;
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word2);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        if (w < n_words) bsi_key_word(found_q, n_found, w);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u64 max_attractor_l,
+               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+    __shared__ u32 aux_s[32 * BSI_BLOCK];
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    if (n_words <= few_words) return;
+    u64 steps = 0, n_acc = 0, n_rej = 0;
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word3);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        if (w >= n_words) continue;
+        bsi_mu_word<false>(found_q, n_found, w, aux_s, ctr);
+        bsi_finish_word<true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
+                              ctr, steps, n_acc, n_rej, aux_s);
+    }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
 }
 
-#endif  // BSI_UNIT 3
+#endif  // BSI_UNIT != 5
+#if BSI_UNIT != 3
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
+    __shared__ u32 aux_s[32 * BSI_BLOCK];
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    if (n_words > few_words) return;
+    const u64 w32 = (n_words + 31) & ~(u64)31;
+    for (;;) {
+        const u64 t = bsi_grab_word(&ctr->next_word2);
+        if (__all_sync(0xFFFFFFFFu, t >= 2 * w32)) break;
+        if (t < w32) {
+            if (t < n_words) bsi_mu_word<true>(found_q, n_found, t, aux_s, ctr);
+        } else if (t - w32 < n_words) {
+            bsi_key_word(found_q, n_found, t - w32);
+        }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T,
+                   u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,
+                   BsiCounters *ctr) {
+    const u64 n_found = *n_found_p;
+    const u64 n_words = (n_found + 31) >> 5;
+    if (n_words > few_words) return;
+    u64 steps = 0, n_acc = 0, n_rej = 0;
+    for (;;) {
+        const u64 w = bsi_grab_word(&ctr->next_word3);
+        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
+        if (w >= n_words) continue;
+        bsi_finish_word<false>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
+                               ctr, steps, n_acc, n_rej, nullptr);
+    }
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
+    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
+}
+
+#endif  // BSI_UNIT != 3
+#endif  // BSI_UNIT 3, 5
 
 #if BSI_UNIT == 0 || BSI_UNIT == 4
 // ---- attractor table: export / merge ------------------------------------------------------------

@@ -119,7 +119,9 @@ typedef struct bsi_plan_opts {
     uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto       */
     uint32_t debug_stats;      /* 1: count filter events (stats->reserved[0] = stage-2 filter entries,
                                   [1] = full compares); costs atomics, for tuning only */
-    uint32_t reserved[8];
+    uint32_t resolve_few_words;/* attract: queue length (words of 32 matched lanes) up to which the
+                                  latency-oriented resolution kernels are used; 0 = auto (32768) */
+    uint32_t reserved[7];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */
