@@ -328,13 +328,19 @@ class Plan:
         check(lib().bsi_attract_table_count(self._h, C.byref(n)))
         return n.value
 
-    def table_read(self):
-        """-> structured array of ATTRACTOR_REC (unsorted)."""
-        n = self.table_count()
-        out = np.zeros(max(n, 1), ATTRACTOR_REC)
-        got = C.c_uint64()
-        check(lib().bsi_attract_table_read(self._h, _ptr(out), max(n, 1), C.byref(got)))
-        return out[:got.value]
+    def table_read(self, first_capacity=1024):
+        """-> structured array of ATTRACTOR_REC (unsorted).  One export when the table fits the
+        first guess; otherwise the call reports the true count and is repeated."""
+        capacity = first_capacity
+        while True:
+            out = np.zeros(capacity, ATTRACTOR_REC)
+            got = C.c_uint64()
+            status = lib().bsi_attract_table_read(self._h, _ptr(out), capacity, C.byref(got))
+            if status == -4 and got.value > capacity:       # BSI_E_CAPACITY: got = records held
+                capacity = int(got.value)
+                continue
+            check(status)
+            return out[:got.value]
 
     def table_export_device(self, dev_ptr, capacity):
         n = C.c_uint64()

@@ -186,6 +186,8 @@ struct bsi_plan {
     CUdevice dev = 0;
     CUcontext ctx = nullptr;
     CUmodule mods[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool mod_cached[6] = {false, false, false, false, false, false};   // owned by the module cache
+    std::string unit_key[6];         // identifies a unit's source (module cache key)
     CUstream own_stream = nullptr, stream = nullptr;
     CUfunction f_dense = nullptr, f_queue = nullptr, f_key = nullptr, f_mu = nullptr,
                f_resolve = nullptr, f_finish = nullptr,
@@ -341,7 +343,7 @@ std::vector<int> choose_filter(const bsi::Model &m, int want, std::vector<int> *
 
 struct UnitResult {
     int status = BSI_OK;
-    std::string error, log;
+    std::string error, log, key;
     std::vector<char> cubin;
 };
 
@@ -351,6 +353,7 @@ UnitResult compile_unit(std::string src) {
     static std::mutex cache_mu;
     static std::map<std::string, std::pair<std::vector<char>, std::string>> cache;
     UnitResult out;
+    out.key = std::to_string(src.size()) + ":" + std::to_string(std::hash<std::string>()(src));
     {
         std::lock_guard<std::mutex> lk(cache_mu);
         auto it = cache.find(src);
@@ -402,8 +405,24 @@ UnitResult compile_unit(std::string src) {
 int compile_plan(bsi_plan *p) {
     StageTimer tm;
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
-    std::vector<int> filter2;
-    std::vector<int> filter = choose_filter(p->m, f_nodes, &filter2, 12);
+    std::vector<int> filter2, filter;
+    {
+        // the activity probe only depends on the rules and the origin fixed nodes: remember it
+        static std::mutex mu;
+        static std::map<std::string, std::pair<std::vector<int>, std::vector<int>>> probes;
+        std::string key = std::to_string(f_nodes) + "|";
+        for (int i = 0; i < p->m.n; ++i) key += p->m.fn[i].key() + ";";
+        for (auto &kv : p->m.fixed) key += "f" + std::to_string(kv.first) + "=" + std::to_string(kv.second);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = probes.find(key);
+        if (it == probes.end()) {
+            filter = choose_filter(p->m, f_nodes, &filter2, 12);
+            if (probes.size() < 256) probes[key] = {filter, filter2};
+        } else {
+            filter = it->second.first;
+            filter2 = it->second.second;
+        }
+    }
     tm.lap("choose_filter");
     p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
     if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
@@ -431,6 +450,7 @@ int compile_plan(bsi_plan *p) {
         if (r.status != BSI_OK && rc == BSI_OK) { rc = r.status; g_err = r.error; }
         if (!r.log.empty()) p->log += r.log + "\n";
         p->cubins[units[i]] = std::move(r.cubin);
+        p->unit_key[units[i]] = r.key;
     }
     tm.lap("nvrtc (parallel units)");
     p->source = "#define BSI_UNIT 0\n" + p->source;       // what bsi_plan_source shows: the whole TU
@@ -452,8 +472,27 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
     if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
     CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
-    for (int u = 1; u <= 5; ++u)
-        if (!p->cubins[u].empty()) CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u].data()));
+    // loaded modules are kept per (device, unit source) for the life of the process: a later plan
+    // for the same network skips cuModuleLoadData / cuModuleUnload (several ms)
+    {
+        static std::map<std::string, CUmodule> loaded;
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        for (int u = 1; u <= 5; ++u) {
+            if (p->cubins[u].empty()) continue;
+            const std::string key = std::to_string(device) + "/" + p->unit_key[u];
+            auto it = loaded.find(key);
+            if (it != loaded.end()) {
+                p->mods[u] = it->second;
+                p->mod_cached[u] = true;
+                continue;
+            }
+            CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u].data()));
+            if (loaded.size() < 128) {
+                loaded[key] = p->mods[u];
+                p->mod_cached[u] = true;
+            }
+        }
+    }
     tm.lap("cuModuleLoadData");
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
     p->stream = p->own_stream;
@@ -587,7 +626,7 @@ void bsi_plan_destroy(bsi_plan *p) {
             tm.lap("destroy: buffers");
             for (CUevent e : p->events) cu().p_cuEventDestroy(e);
             if (p->own_stream) cu().p_cuStreamDestroy(p->own_stream);
-            for (CUmodule m : p->mods) if (m) cu().p_cuModuleUnload(m);
+            for (int u = 0; u < 6; ++u) if (p->mods[u] && !p->mod_cached[u]) cu().p_cuModuleUnload(p->mods[u]);
             tm.lap("destroy: module/stream");
         }
     }
