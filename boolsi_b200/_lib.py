@@ -156,6 +156,13 @@ def words_from_code(code, kw):
     return np.array([(code >> (64 * j)) & (2 ** 64 - 1) for j in range(kw)], np.uint64)
 
 
+def states_from_word_rows(rows, n_nodes):
+    """uint64 [n_states, key_words] -> list of n_states lists of n_nodes bools (bit i = node i)."""
+    rows = np.ascontiguousarray(rows, dtype='<u8')
+    bits = np.unpackbits(rows.view(np.uint8).reshape(rows.shape[0], -1), axis=1, bitorder='little')
+    return bits[:, :n_nodes].astype(bool).tolist()
+
+
 def code_from_words(words):
     v = 0
     for j, w in enumerate(words):
@@ -362,9 +369,10 @@ class Plan:
         check(lib().bsi_attractor_states(self._h, _ptr(kwords), int(lam), _ptr(out)))
         return [code_from_words(row) for row in out]
 
-    def attractor_states_batch(self, keys_and_lams):
-        """[(key, lam), ...] -> [[state codes, key first], ...]; one launch per power-of-two
-        length class so that a long cycle does not inflate the buffers of the short ones."""
+    def attractor_states_batch(self, keys_and_lams, as_words=False):
+        """[(key, lam), ...] -> [[state codes, key first], ...] (or, with `as_words`, uint64 arrays
+        [lam, key_words]); one launch per power-of-two length class so that a long cycle does not
+        inflate the buffers of the short ones."""
         out = [None] * len(keys_and_lams)
         groups = {}
         for pos, (key, lam) in enumerate(keys_and_lams):
@@ -378,7 +386,7 @@ class Plan:
             check(lib().bsi_attractor_states_batch(self._h, _ptr(keys), len(members), n_states, _ptr(buf)))
             for row, pos in enumerate(members):
                 lam = int(keys_and_lams[pos][1])
-                out[pos] = [code_from_words(w) for w in buf[row, :lam]]
+                out[pos] = buf[row, :lam].copy() if as_words else [code_from_words(w) for w in buf[row, :lam]]
         return out
 
     # ---- simulate / target -----------------------------------------------------------------

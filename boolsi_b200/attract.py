@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from .db import init_attractor_db_structure
-from .problems import shard_range, state_from_code
+from .problems import shard_range
 
 
 
@@ -93,9 +93,9 @@ class AttractEngine:
             rows.append((_lib.code_from_words(r['key'][:self.plan.kw]), int(r['n']), int(r['sum_l']),
                          int(r['sum_l2']), int(r['lam'])))
         rows.sort(key=lambda x: (-x[1], x[0]))
-        orbits = self.plan.attractor_states_batch([(key, lam) for key, _, _, _, lam in rows])
-        return [AggregatedAttractor(key, [state_from_code(c, n_nodes) for c in codes], n, s1, s2)
-                for (key, n, s1, s2, lam), codes in zip(rows, orbits)]
+        orbits = self.plan.attractor_states_batch([(key, lam) for key, _, _, _, lam in rows], as_words=True)
+        return [AggregatedAttractor(key, _lib.states_from_word_rows(words, n_nodes), n, s1, s2)
+                for (key, n, s1, s2, lam), words in zip(rows, orbits)]
 
 
 def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_problem,

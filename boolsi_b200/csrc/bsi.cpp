@@ -166,12 +166,12 @@ struct DevBuf {
 std::mutex g_dev_mu;
 std::map<int, CUcontext> g_ctx;
 
-// Freed device buffers >= 1 MiB are parked per device and reused by later plans (the found queue
-// of a 2^26-state chunk is 3 GB; cuMemAlloc/cuMemFree of that size cost tens of ms).
+// Freed device buffers are parked per device and reused by later plans (the found queue of a
+// 2^26-state chunk is 3 GB; cuMemAlloc/cuMemFree cost from a fraction of a ms to tens of ms).
 struct Parked { CUdeviceptr p; size_t bytes; };
 std::map<int, std::vector<Parked>> g_pool;
 size_t g_pool_bytes = 0;
-constexpr size_t kPoolMinBytes = (size_t)1 << 20, kPoolMaxBytes = (size_t)24 << 30;
+constexpr size_t kPoolMinBytes = 256, kPoolMaxBytes = (size_t)24 << 30;
 
 }  // namespace
 
@@ -248,6 +248,11 @@ int ensure(bsi_plan *p, DevBuf &b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return BSI_OK;
     give_back(p->device, b);
     size_t want = std::max<size_t>(bytes, 256);
+    if (want < ((size_t)1 << 20)) {          // small buffers: power-of-two sizes, so that they get reused
+        size_t r = 256;
+        while (r < want) r <<= 1;
+        want = r;
+    }
     if (want >= kPoolMinBytes) {
         // best fit among the parked buffers of this device, wasting at most 2x
         std::lock_guard<std::mutex> lk(g_dev_mu);

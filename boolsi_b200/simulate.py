@@ -4,7 +4,7 @@ import logging
 
 from . import _lib
 from .db import init_simulation_db_structure
-from .problems import decode_simulation_problem, state_from_code
+from .problems import decode_simulation_problem
 
 
 def count_perturbations(perturbed_nodes_by_t):
@@ -23,7 +23,7 @@ class Simulation:
 
 
 def states_from_words(rows, n_nodes):
-    return [state_from_code(_lib.code_from_words(words), n_nodes) for words in rows]
+    return _lib.states_from_word_rows(rows, n_nodes)
 
 
 def store_simulations(db_conn, simulations):

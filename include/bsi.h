@@ -151,7 +151,7 @@ typedef struct bsi_run_stats {
 int bsi_abi_version(void);
 const char *bsi_last_error(void);
 int bsi_device_count(int *count);
-/* Plans park freed device buffers >= 1 MiB for reuse by later plans of the same process (and keep
+/* Plans park freed device buffers for reuse by later plans of the same process (and keep
  * the device's primary context retained); this returns the parked memory to the driver. */
 int bsi_release_cached_memory(void);
 
