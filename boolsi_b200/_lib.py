@@ -31,7 +31,7 @@ EXPORTS = [
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
     'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
-    'bsi_attractor_states_batch',
+    'bsi_attractor_states_batch', 'bsi_attract_schedule',
 ]
 
 
@@ -134,6 +134,7 @@ def lib():
         L.bsi_measure_lop3_peak.argtypes = [i, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.POINTER(i)]
         L.bsi_measure_update_rate.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.bsi_attract_schedule.argtypes = [u64, p, p, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         _lib = L
     return _lib
 
@@ -417,6 +418,15 @@ class Plan:
                                    _ptr(hit_index), _ptr(hit_t), capacity, C.byref(got),
                                    C.byref(st)))
         return hit_index[:got.value], hit_t[:got.value], st.as_dict()
+
+
+def attract_schedule(horizon):
+    """-> (checkpoint times, slots, end, first_final) of a detection round with this horizon."""
+    times, slots = np.zeros(96, np.uint32), np.zeros(96, np.uint32)
+    n, end, ff = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    check(lib().bsi_attract_schedule(int(horizon), _ptr(times), _ptr(slots), 96, C.byref(n), C.byref(end),
+                                     C.byref(ff)))
+    return times[:n.value].tolist(), slots[:n.value].tolist(), end.value, ff.value
 
 
 def release_cached_memory():

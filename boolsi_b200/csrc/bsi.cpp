@@ -638,6 +638,21 @@ void bsi_plan_destroy(bsi_plan *p) {
     delete p;
 }
 
+int bsi_attract_schedule(uint64_t horizon, uint32_t *ck_time, uint32_t *ck_slot, uint32_t cap,
+                         uint32_t *n_ck, uint32_t *end, uint32_t *first_final) {
+    if (horizon == 0 || horizon > ((uint64_t)1 << 30)) return fail(BSI_E_ARG, "horizon out of range");
+    Sched s = make_sched(horizon);
+    if (n_ck) *n_ck = s.n_ck;
+    if (end) *end = s.end;
+    if (first_final) *first_final = s.first_final;
+    if (s.n_ck > cap) return fail(BSI_E_CAPACITY, "schedule has %u checkpoints", s.n_ck);
+    for (uint32_t i = 0; i < s.n_ck; ++i) {
+        if (ck_time) ck_time[i] = s.ck_time[i];
+        if (ck_slot) ck_slot[i] = s.ck_slot[i];
+    }
+    return BSI_OK;
+}
+
 int bsi_release_cached_memory(void) {
     if (!cu().ok) return BSI_OK;
     std::map<int, std::vector<Parked>> drop;

@@ -192,6 +192,12 @@ int bsi_compile_only(const bsi_network_desc *network, const bsi_space_desc *spac
                      const bsi_target_desc *target, const bsi_plan_opts *opts,
                      uint64_t *cubin_bytes, char *log, uint64_t log_cap);
 
+/* The checkpoint schedule a detection round with this horizon uses (times relative to the last
+ * perturbation; see the header comment of bsi_template.cuh): exposed so that the proof obligation
+ * -- every trajectory with mu + lambda <= horizon is matched by time `end` -- can be tested. */
+int bsi_attract_schedule(uint64_t horizon, uint32_t *ck_time, uint32_t *ck_slot, uint32_t cap,
+                         uint32_t *n_ck, uint32_t *end, uint32_t *first_final);
+
 /* ---- attract (replaces attract_master's simulation + collection stages, attract.py:67-138) - */
 /* Runs problems [idx_begin, idx_end) and ACCUMULATES into the plan's device attractor table. */
 int bsi_attract_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
