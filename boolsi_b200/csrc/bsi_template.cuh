@@ -1144,48 +1144,67 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
         }
         u32 started = 0u;
         u32 alive = valid & ~hit;
-        for (u64 t = 0;; ++t) {
-            // lanes whose perturbations are all carried out by time t
-            if (t <= BSI_LP_MAX) {
-#pragma unroll 1
-                for (u32 l = 0; l < 32; ++l)
-                    if (((valid >> l) & 1u) && lp_s[l * BSI_BLOCK + threadIdx.x] == (u32)t) started |= 1u << l;
-            }
-            if (pass == 0) {
-                u32 acc = ~(alive & started);
-                BSI_CMP_TARGET(acc, a)
-                u32 m_ = ~acc;
-                if (m_) {
-                    hit |= m_;
-                    alive &= ~m_;
-                    while (m_) {
-                        u32 l_ = __ffs(m_) - 1;
-                        m_ &= m_ - 1;
-                        th_s[l_ * BSI_BLOCK + threadIdx.x] = (u32)t;
-                    }
-                }
-                if (t >= T || (!alive && t >= BSI_LP_MAX)) break;
-            } else {
-                if (t >= T) break;
-                u32 p_ = ~(alive & started), q_ = 0u;
-                BSI_CMP_FILTER(p_, q_, a, c)
-                p_ |= q_;
-                if (p_ != 0xFFFFFFFFu) {
-                    BSI_CMP_REST(p_, a, c)
-                    u32 m_ = ~p_;
-                    closed |= m_;
-                    alive &= ~m_;
-                }
-                if (!alive) break;
-            }
+        // one time step of the test on state X at time TT; sets stop_ when the pass is over
+#define BSI_TCHECK(X, TT)                                                         \
+    {                                                                             \
+        const u64 t_ = (TT);                                                      \
+        /* lanes whose perturbations are all carried out by time t */               \
+        if (BSI_LANES_UNIFORM) {                                                  \
+            if (t_ == BSI_LP_ORIGIN) started = valid;                             \
+        } else if (t_ <= BSI_LP_MAX) {                                            \
+            _Pragma("unroll 1") for (u32 l = 0; l < 32; ++l)                      \
+                if (((valid >> l) & 1u) && lp_s[l * BSI_BLOCK + threadIdx.x] == (u32)t_) started |= 1u << l; \
+        }                                                                         \
+        if (pass == 0) {                                                          \
+            u32 acc = ~(alive & started);                                         \
+            BSI_CMP_TARGET(acc, X)                                                \
+            u32 m_ = ~acc;                                                        \
+            if (m_) {                                                             \
+                hit |= m_;                                                        \
+                alive &= ~m_;                                                     \
+                while (m_) {                                                      \
+                    u32 l_ = __ffs(m_) - 1;                                       \
+                    m_ &= m_ - 1;                                                 \
+                    th_s[l_ * BSI_BLOCK + threadIdx.x] = (u32)t_;                 \
+                }                                                                 \
+            }                                                                     \
+            stop_ = t_ >= T || (!alive && t_ >= BSI_LP_MAX);                      \
+        } else {                                                                  \
+            stop_ = t_ >= T;                                                      \
+            if (!stop_) {                                                         \
+                u32 p_ = ~(alive & started), q_ = 0u;                             \
+                BSI_CMP_FILTER(p_, q_, X, c)                                      \
+                p_ |= q_;                                                         \
+                if (p_ != 0xFFFFFFFFu) {                                          \
+                    BSI_CMP_REST(p_, X, c)                                        \
+                    u32 m_ = ~p_;                                                 \
+                    closed |= m_;                                                 \
+                    alive &= ~m_;                                                 \
+                }                                                                 \
+                stop_ = !alive;                                                   \
+            }                                                                     \
+        }                                                                         \
+    }
+        // two steps per iteration (a -> b -> a), so that no step needs a register copy
+        bool stop_ = false, cur_is_b = false;
+        for (u64 t = 0;; t += 2) {
+            BSI_TCHECK(a, t)
+            if (stop_) { cur_is_b = false; break; }
             BSI_UPDATE(b, a)
             BSI_PERTURB(b, (t + 1))
-            BSI_FOR_NODES(BSI_COPY_AB)
+            ++dev_steps;
+            BSI_TCHECK(b, t + 1)
+            if (stop_) { cur_is_b = true; break; }
+            BSI_UPDATE(a, b)
+            BSI_PERTURB(a, (t + 2))
             ++dev_steps;
         }
+#undef BSI_TCHECK
         if (pass == 0) {
             if (!check_closure || !alive) break;
-            BSI_FOR_NODES(BSI_COPY_CA)
+#define BSI_COPY_CB2(i) c##i = b##i;
+            if (cur_is_b) { BSI_FOR_NODES(BSI_COPY_CB2) } else { BSI_FOR_NODES(BSI_COPY_CA) }
+#undef BSI_COPY_CB2
         }
     }
 
