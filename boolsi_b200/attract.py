@@ -61,6 +61,7 @@ class AttractEngine:
         totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
         if self.world > 1:
             totals = self._merge_over_ranks(st)
+            st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
         self.totals = totals
         return st
 

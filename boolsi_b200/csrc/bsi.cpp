@@ -838,10 +838,14 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
             if ((rc = read_counters(p, &c))) return rc;
             if (c.n_retry == 0) break;
             if (H >= kMaxH) return fail(BSI_E_UNSUPPORTED, "a trajectory did not close within 2^30 steps");
+            // next horizon: x4 -- or, when most lanes are still open (chaotic regime), straight to
+            // the cap (finite max_t) / x16 (no cap): every round replays its lanes from t = 0
+            const bool mostly_open = c.n_retry * 2 > n_in;
             n_in = c.n_retry;
             dense = false;
             which ^= 1;
-            H = std::min(H * 4, kMaxH);
+            if (mostly_open) H = T != BSI_INF ? T : std::min(H * 16, kMaxH);
+            else H = std::min(H * 4, kMaxH);
         }
         b = e;
     }

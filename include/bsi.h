@@ -137,7 +137,9 @@ typedef struct bsi_run_stats {
     uint64_t n_problems;       /* problems processed by this call */
     uint64_t n_found;          /* attract: problems whose attractor passed both caps; target: hits */
     uint64_t n_without;        /* attract: problems with no attractor within the caps */
-    uint64_t steps;            /* sum over problems of the reference's stop time (model.py:235) */
+    uint64_t steps;            /* sum over problems of the reference's stop time (model.py:235);
+                                  target mode: exact for hits, max_t for the others (an upper bound
+                                  when a trajectory closes its cycle before max_t without a hit) */
     uint64_t device_steps;     /* 32-lane word-steps actually executed by the main kernels */
     uint64_t launches;         /* kernels launched by this call */
     uint64_t rounds;           /* attract: detection rounds (horizon doublings + 1) */
