@@ -844,7 +844,7 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
             n_in = c.n_retry;
             dense = false;
             which ^= 1;
-            if (mostly_open) H = T != BSI_INF ? T : std::min(H * 16, kMaxH);
+            if (mostly_open) H = T != BSI_INF ? std::min(T, kMaxH) : std::min(H * 16, kMaxH);
             else H = std::min(H * 4, kMaxH);
         }
         b = e;

@@ -279,3 +279,17 @@ def test_attractor_table_overflow_is_reported():
     with _lib.Plan(pk, _lib.MODE_ATTRACT, table_log2_slots=16) as plan:
         st = plan.attract_run(0, 1 << n, inf, inf)
         assert plan.table_count() == 1 << n and st['n_found'] == 1 << n and st['steps'] == 1 << n
+
+
+def test_attract_long_cap_goes_through_several_rounds():
+    """max_t beyond the first horizon in the chaotic regime: rounds 1024 -> cap (most lanes stay
+    open), results equal to the oracle's."""
+    cfg = synth.random_attract_problem(64, 3, 2, n_free=12)
+    pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                            cfg['origin simulation problem'], cfg['simulation problem variations'])
+    want_rows, want_steps, want_without = _oracle_table(cfg, 3000, inf, 0, 1 << 12)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT) as plan:
+        st = plan.attract_run(0, 1 << 12, 3000, inf)
+        assert st['rounds'] >= 2
+        assert _table_rows(plan) == want_rows
+        assert (st['steps'], st['n_without']) == (want_steps, want_without)
