@@ -31,11 +31,21 @@ def target_master(mpi_comm, n_simulation_problem_batches_per_process, origin_sim
     with _lib.Plan(packed, _lib.MODE_TARGET, device=device, target=tgt) as plan:
         hit_index, hit_t, _ = plan.target_run(0, packed.n_problems, max_t,
                                               n_simulations_to_reach_target_substate)
-        for index, t in zip(hit_index, hit_t):
-            rows, _ = plan.simulate_list([int(index)], int(t))
+        # trajectories of the reported hits: plain iteration up to the hit time (target.py:129-131),
+        # regenerated in batches -- one launch per power-of-two class of hit times
+        states_by_pos = [None] * len(hit_index)
+        groups = {}
+        for pos, t in enumerate(hit_t):
+            groups.setdefault(int(t).bit_length(), []).append(pos)
+        for _, members in sorted(groups.items()):
+            t_max = max(int(hit_t[pos]) for pos in members)
+            rows, _ = plan.simulate_list([int(hit_index[pos]) for pos in members], t_max)
+            for row, pos in zip(rows, members):
+                states_by_pos[pos] = states_from_words(row[:int(hit_t[pos]) + 1], packed.n_nodes)
+        for pos, index in enumerate(hit_index):
             _, fixed, perturbed = decode_simulation_problem(int(index), origin_simulation_problem,
                                                             simulation_problem_variations)
-            simulations.append(Simulation(states_from_words(rows[0], packed.n_nodes), fixed, perturbed))
+            simulations.append(Simulation(states_by_pos[pos], fixed, perturbed))
     store_simulations(db_conn, simulations)
     log.info('{} simulations reach target state.'.format(db_conn.root.n_simulations()))
     return db_conn.root.n_simulations()
