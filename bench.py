@@ -41,8 +41,9 @@ def config_dict(n_free, n_gpus):
             'n_problems': 2 ** n_free, 'max_t': MAX_T,
             'parallelism': 'index space sharded over %d GPU(s), one NCCL all_gather of attractor tables' % n_gpus,
             'l2_policy': 'no input buffers exist: initial states are generated on the device from the '
-                         'problem index; state lives in registers; the 38 MB checkpoint scratch is rewritten '
-                         'every step, so nothing is carried between timed iterations'}
+                         'problem index; state lives in registers and checkpoints in shared memory; the found '
+                         'queue (20 MB) and the attractor table are rewritten every step, so nothing is carried '
+                         'between timed iterations'}
 
 
 # ---- CPU side -----------------------------------------------------------------------------------
