@@ -7,4 +7,4 @@ call sites they drop into); everything between is libbsi's CUDA path.  No CPU fa
 from .attract import AggregatedAttractor, AttractEngine, attract_master, attract_sharded  # noqa: F401
 from .db import ResultStore, init_attractor_db_structure, init_simulation_db_structure  # noqa: F401
 from .simulate import Simulation, simulate_master  # noqa: F401
-from .target import target_master  # noqa: F401
+from .target import merge_sharded_hits, target_master, target_sharded  # noqa: F401

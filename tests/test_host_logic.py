@@ -105,3 +105,30 @@ def test_two_rank_exchange_over_gloo(tmp_path, capacity):
         got = np.load(os.path.join(str(tmp_path), 'r%d.npy' % r), allow_pickle=True).tolist()
         assert got[:-1] == want                       # every rank holds the complete, identical table
         assert got[-1][1] == rec['steps']
+
+
+@pytest.mark.parametrize('n_to_find', [inf, 1, 7, 10 ** 9])
+def test_sharded_target_hits_merge_in_enumeration_order(n_to_find):
+    """The N>1 `target` path without GPUs: per-shard hit lists (from the C oracle) merged by
+    `merge_sharded_hits` equal the single-range answer, for every rank count."""
+    from boolsi_b200.target import merge_sharded_hits
+    cfg = synth.random_target_problem(24, 3, 1, n_free=11, n_fixed=2, n_perturbed=2, n_perturbation_times=3,
+                                      max_perturbation_t=9, n_target_nodes=3)
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    rec = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 60)
+    want = np.nonzero(rec['reached'])[0]
+    assert len(want) > 10
+    cap = len(want) if n_to_find == inf else min(len(want), n_to_find)
+    for world in (1, 2, 3, 8):
+        per_rank = []
+        for r in range(world):
+            lo, hi = problems.shard_range(sp.n_problems, r, world)
+            sub = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 60, lo, hi)
+            hits = np.nonzero(sub['reached'])[0]
+            keep = hits if n_to_find == inf else hits[:n_to_find]
+            per_rank.append((keep + lo, sub['stop_t'][keep], len(hits)))
+        index, t, total = merge_sharded_hits(per_rank, n_to_find)
+        assert total == len(want)
+        assert [int(i) for i in index] == [int(i) for i in want[:cap]]
+        assert [int(x) for x in t] == [int(rec['stop_t'][i]) for i in want[:cap]]
