@@ -615,6 +615,14 @@ bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final
 // ---------------------------------------------------------------------------------------------
 #if BSI_UNIT == 0 || BSI_UNIT == 3 || BSI_UNIT == 5
 
+// Which records of the found queue form "word" w of the resolution kernels: words come in groups
+// of 32 (one warp), a group owns 1024 consecutive records, and lane l of the group's t-th word is
+// record 1024 g + 32 l + t -- so that, for a fixed lane, the 32 threads of a warp read 32
+// CONSECUTIVE records (coalesced 48-byte structs) instead of records 1.5 KB apart.
+#define BSI_Q(w, l) ((((w) & ~31ull) << 5) + ((u64)(l) << 5) + ((w) & 31ull))
+// number of words to hand out for n records (whole groups)
+#define BSI_QWORDS(n) ((((n) + 1023ull) >> 10) << 5)
+
 // Canonical key = lexicographic minimum over the cycle with node N-1 most significant, i.e. the
 // minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
 // the cycle of found_q[32w + l] from y; walking more than lambda steps only revisits cycle
@@ -628,7 +636,7 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
         u64 cw_[32][BSI_KW];
 #pragma unroll 1
         for (u32 l = 0; l < 32; ++l) {
-            u64 q = (w << 5) + l;
+            const u64 q = BSI_Q(w, l);
             const bool in = q < n_found;
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = in ? found_q[q].y[i] : 0ull;
@@ -670,7 +678,7 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
         for (u32 l = 0; l < 32; ++l) {
             if ((valid >> l) & 1u) {
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) found_q[(w << 5) + l].key[i] = cw_[l][i];
+                for (int i = 0; i < BSI_KW; ++i) found_q[BSI_Q(w, l)].key[i] = cw_[l][i];
             }
         }
     }
@@ -682,30 +690,56 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
 // a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
 // walks P(j); three register sets rotate so that no step needs a copy.
 // Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
-template <bool WRITE_PAD>
+struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it runs in the same kernel
+    u64 key[32][BSI_KW];
+    u32 lam[32], c0[32];
+};
+
+template <bool WRITE_PAD, bool KEEP>
 __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
-                                            BsiCounters *ctr) {
+                                            BsiCounters *ctr, BsiKeep *keep) {
     const u32 tid = threadIdx.x;
     {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
         u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u;
-        u64 cw_[32][BSI_KW];
+        // one pass over the 32 records of this word: every field that is needed later goes to
+        // (thread-interleaved, hence coalesced) local arrays
+        u64 cw_[32][BSI_KW], cz_[32][BSI_KW], cx_[32][BSI_KW];
 #pragma unroll 1
         for (u32 l = 0; l < 32; ++l) {
-            u64 q = (w << 5) + l;
+            const u64 q = BSI_Q(w, l);
+            u64 x_[BSI_KW];
 #pragma unroll
-            for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = q < n_found ? found_q[q].y[i] : 0ull;
+            for (int i = 0; i < BSI_KW; ++i) { cw_[l][i] = 0ull; cz_[l][i] = 0ull; x_[i] = 0ull; }
             if (q < n_found) {
+                const BsiFound r = found_q[q];
                 valid |= 1u << l;
-                const u32 lam = found_q[q].lam, c = found_q[q].c, c0 = found_q[q].c0;
-                const u32 adv = (lam - (c - c0) % lam) % lam;
+                const u32 adv = (r.lam - (r.c - r.c0) % r.lam) % r.lam;
                 aux_s[l * BSI_BLOCK + tid] = adv;
                 adv_max = max(adv_max, adv);
-                c_max = max(c_max, c - c0);          // the walk is at most c - c0 steps long
-                if (c0 == 0u) from_idx |= 1u << l;
+                c_max = max(c_max, r.c - r.c0);      // the walk is at most c - c0 steps long
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = r.y[i];
+                if (r.c0 == 0u) {
+                    from_idx |= 1u << l;
+                    u64 lp_lane_ = 0;
+                    BSI_LANE_SETUP(l, r.idx, x_)
+                    (void)lp_lane_;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) cz_[l][i] = r.z[i];
+                }
+                if (KEEP) {
+                    keep->lam[l] = r.lam;
+                    keep->c0[l] = r.c0;
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) keep->key[l][i] = r.key[i];
+                }
             }
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
         BSI_PACK(b, cw_)
         // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
@@ -738,33 +772,12 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             BSI_FOR_NODES(BSI_COPY_CB)
             BSI_FOR_NODES(BSI_ZERO_A)
             if (from_idx) {
-#pragma unroll 1
-                for (u32 l = 0; l < 32; ++l) {
-                    u64 q = (w << 5) + l;
-                    u64 c_[BSI_KW];
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) c_[i] = 0ull;
-                    if ((from_idx >> l) & 1u) {
-                        u64 lp_lane_ = 0;
-                        BSI_LANE_SETUP(l, found_q[q].idx, c_)
-                        (void)lp_lane_;
-                    }
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = c_[i];
-                }
-                BSI_PACK(a, cw_)
+                BSI_PACK(a, cx_)
                 BSI_PREFIX(BSI_LP_ORIGIN)
                 BSI_FOR_NODES(BSI_MASK_A)
             }
             if (valid & ~from_idx) {
-#pragma unroll 1
-                for (u32 l = 0; l < 32; ++l) {
-                    u64 q = (w << 5) + l;
-                    const bool use_z = ((valid & ~from_idx) >> l) & 1u;
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = use_z ? found_q[q].z[i] : 0ull;
-                }
-                BSI_PACK(b, cw_)
+                BSI_PACK(b, cz_)
                 BSI_FOR_NODES(BSI_OR_AB)
             }
             BSI_FOR_NODES(BSI_COPY_BC)
@@ -809,7 +822,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         if (WRITE_PAD) {
 #pragma unroll 1
             for (u32 l = 0; l < 32; ++l)
-                if ((valid >> l) & 1u) found_q[(w << 5) + l].pad = found_q[(w << 5) + l].c0 + aux_s[l * BSI_BLOCK + tid];
+                if ((valid >> l) & 1u) found_q[BSI_Q(w, l)].pad = found_q[BSI_Q(w, l)].c0 + aux_s[l * BSI_BLOCK + tid];
         }
 
     }
@@ -818,31 +831,53 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 // Acceptance (mu + lambda <= T, lambda <= max_attractor_l; reference attract.py:287-300) and
 // aggregation into the attractor table (attract.py:374-402) of the 32 lanes of word w; lanes of
 // one thread with equal keys are added once.
-template <bool FROM_AUX>
+template <bool FROM_KEEP>
 __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_found, u64 w, u64 T,
                                                 u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
                                                 u32 log2_slots, BsiCounters *ctr, u64 &steps,
-                                                u64 &n_acc, u64 &n_rej, const u32 *aux_s) {
+                                                u64 &n_acc, u64 &n_rej, const u32 *aux_s,
+                                                BsiKeep *keep) {
     {
-        const u64 left = n_found - (w << 5);
-        u32 todo = left >= 32 ? 0xFFFFFFFFu : ((1u << (u32)left) - 1u);
+        u32 todo = 0u;
+        if (FROM_KEEP) {
+            // same kernel as the mu walk: keys / lambda / c0 were kept, mu - c0 is in aux_s
+#pragma unroll 1
+            for (u32 l = 0; l < 32; ++l)
+                if (BSI_Q(w, l) < n_found) todo |= 1u << l;
+        } else {
+            // another kernel: one pass over the records; mu itself is in the pad field
+#pragma unroll 1
+            for (u32 l = 0; l < 32; ++l) {
+                const u64 q = BSI_Q(w, l);
+                if (q < n_found) {
+                    const BsiFound r = found_q[q];
+                    todo |= 1u << l;
+                    keep->lam[l] = r.lam;
+                    keep->c0[l] = r.pad;
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) keep->key[l][i] = r.key[i];
+                }
+            }
+        }
         // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
         while (todo) {
             const u32 l0 = __ffs(todo) - 1;
-            const BsiFound r0 = found_q[(w << 5) + l0];
+            u64 key0[BSI_KW];
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) key0[i] = keep->key[l0][i];
+            const u32 lam0 = keep->lam[l0];
             u64 n = 0, s1 = 0, s2 = 0;
             u32 rest = todo;
             while (rest) {
                 const u32 l = __ffs(rest) - 1;
                 rest &= rest - 1;
-                const BsiFound *r = found_q + ((w << 5) + l);
                 bool same = true;
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) same = same && (r->key[i] == r0.key[i]);
+                for (int i = 0; i < BSI_KW; ++i) same = same && (keep->key[l][i] == key0[i]);
                 if (!same) continue;
                 todo &= ~(1u << l);
-                const u64 mu = FROM_AUX ? (u64)r->c0 + aux_s[l * BSI_BLOCK + threadIdx.x] : (u64)r->pad;
-                const u64 lam = r->lam;
+                const u64 mu = (u64)keep->c0[l] + (FROM_KEEP ? aux_s[l * BSI_BLOCK + threadIdx.x] : 0u);
+                const u64 lam = keep->lam[l];
                 if (mu + lam <= T) {                     // the loop stops at t = mu + lambda (model.py:201)
                     steps += BSI_LP_ORIGIN + mu + lam;
                     if (lam <= max_attractor_l) {        // attract.py:294
@@ -857,7 +892,7 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                 }
             }
             if (n) {
-                bsi_table_add(table, log2_slots, r0.key, n, s1, s2, r0.lam, ctr);
+                bsi_table_add(table, log2_slots, key0, n, s1, s2, lam0, ctr);
                 n_acc += n;
             }
         }
@@ -876,8 +911,8 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
     const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    if (n_words <= few_words) return;
+    if (((n_found + 31) >> 5) <= few_words) return;
+    const u64 n_words = BSI_QWORDS(n_found);
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word2);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
@@ -890,16 +925,17 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    if (n_words <= few_words) return;
+    if (((n_found + 31) >> 5) <= few_words) return;
+    const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiKeep keep;
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w >= n_words) continue;
-        bsi_mu_word<false>(found_q, n_found, w, aux_s, ctr);
+        if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
+        bsi_mu_word<false, true>(found_q, n_found, w, aux_s, ctr, &keep);
         bsi_finish_word<true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
-                              ctr, steps, n_acc, n_rej, aux_s);
+                              ctr, steps, n_acc, n_rej, aux_s, &keep);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
@@ -912,15 +948,14 @@ extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    if (n_words > few_words) return;
-    const u64 w32 = (n_words + 31) & ~(u64)31;
+    if (((n_found + 31) >> 5) > few_words) return;
+    const u64 w32 = BSI_QWORDS(n_found);             // a multiple of 32
     for (;;) {
         const u64 t = bsi_grab_word(&ctr->next_word2);
         if (__all_sync(0xFFFFFFFFu, t >= 2 * w32)) break;
         if (t < w32) {
-            if (t < n_words) bsi_mu_word<true>(found_q, n_found, t, aux_s, ctr);
-        } else if (t - w32 < n_words) {
+            if (BSI_Q(t, 0) < n_found) bsi_mu_word<true, false>(found_q, n_found, t, aux_s, ctr, nullptr);
+        } else if (t < 2 * w32 && BSI_Q(t - w32, 0) < n_found) {
             bsi_key_word(found_q, n_found, t - w32);
         }
     }
@@ -931,15 +966,16 @@ bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words,
                    u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,
                    BsiCounters *ctr) {
     const u64 n_found = *n_found_p;
-    const u64 n_words = (n_found + 31) >> 5;
-    if (n_words > few_words) return;
+    if (((n_found + 31) >> 5) > few_words) return;
+    const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiKeep keep;
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w >= n_words) continue;
+        if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
         bsi_finish_word<false>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
-                               ctr, steps, n_acc, n_rej, nullptr);
+                               ctr, steps, n_acc, n_rej, nullptr, &keep);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
