@@ -765,7 +765,7 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
     const size_t found_bytes = 24 + 24 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    const size_t scratch_bytes = (size_t)main_grid * p->block * (96 + 128 * p->m.kw) * sizeof(uint32_t);
+    const size_t scratch_bytes = (size_t)main_grid * p->block * 96 * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));

@@ -241,7 +241,8 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // dynamic shared memory of the main kernel: the three checkpoint slots in full,
 // u32 ck[3][N][BLOCK] (48 KB per 64-thread block at N = 64; four blocks per SM fit).  The
 // per-thread scratch in global memory (sized by the persistent grid) only holds the detection
-// records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32], u64 y[KW][32], u64 z[KW][32].
+// records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32] (the matched states
+// themselves stay in shared memory / in a bit-sliced latch until the end of the word).
 extern __shared__ __align__(16) unsigned char bsi_smem[];
 
 // full compare of a state held in local memory with a checkpoint in the scratch: lanes of
@@ -259,46 +260,23 @@ __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u32 
 // (= the checkpoint itself) and the previous checkpoint are extracted from the scratch at the end
 // of the word, when all threads of the warp do so together instead of one diverged thread now.
 #define BSI_DEFERRED 0x80000000u
-__device__ __forceinline__ void bsi_record(const u32 *xs, u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s,
-                                           u64 *y_s, u64 sstride, const u32 *prev_ck, u32 prev_t,
-                                           u32 slot, bool deferred) {
+// A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten)
+// latches the matched lanes' state bit-sliced: yl[i] takes the bits of xs[i] in the lanes of m.
+// One rolled pass over the nodes per event, however many lanes it has; the per-lane state codes
+// come out of one 32x32-transpose pass at the end of the word.
+__device__ __forceinline__ void bsi_record(const u32 *xs, u32 *yl, u32 m, u32 lam, u32 c, u32 *lam_s,
+                                           u32 *c_s, u64 sstride, u32 slot, bool deferred) {
     u32 *c0_s = c_s + 32ull * sstride;
-    u64 *z_s = y_s + (u64)BSI_KW * 32ull * sstride;
+    if (!deferred) {
+#pragma unroll 8
+        for (int i = 0; i < BSI_N; ++i) yl[i] = (yl[i] & ~m) | (xs[i] & m);
+    }
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
-        if (deferred) {
-            lam_s[l * sstride] = lam;
-            c_s[l * sstride] = c;
-            c0_s[l * sstride] = BSI_DEFERRED | slot;
-            continue;
-        }
-        u64 code[BSI_KW];
-#pragma unroll
-        for (int k = 0; k < BSI_KW; ++k) code[k] = 0ull;
-#pragma unroll
-        for (int k = 0; k < BSI_KW; ++k) {
-#pragma unroll 8
-            for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
-                code[k] |= (u64)((xs[i] >> l) & 1u) << (i & 63);
-        }
         lam_s[l * sstride] = lam;
         c_s[l * sstride] = c;
-#pragma unroll
-        for (int k = 0; k < BSI_KW; ++k) y_s[(k * 32 + l) * sstride] = code[k];
-        // a matched final checkpoint s >= 1 implies mu > c_(s-1) (slot s-1 stays armed and would
-        // have matched earlier): ship that state as the start of the mu walk
-        c0_s[l * sstride] = prev_ck ? prev_t : 0u;
-        if (prev_ck) {
-#pragma unroll
-            for (int k = 0; k < BSI_KW; ++k) {
-                u64 z = 0ull;
-#pragma unroll 8
-                for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
-                    z |= (u64)((prev_ck[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
-                z_s[(k * 32 + l) * sstride] = z;
-            }
-        }
+        c0_s[l * sstride] = deferred ? (BSI_DEFERRED | slot) : 0u;
     }
 }
 
@@ -317,7 +295,6 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     // detection records of this thread's 32 lanes (rarely written), in global memory
     u32 *const lam_s = scratch + gtid;                                // [32][sstride]
     u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride], then c0 [32]
-    u64 *const y_s = (u64 *)(scratch + 96ull * sstride) + gtid;       // y, z: [2][KW][32][sstride]
     u64 dev_steps = 0, n_without = 0, ref_steps = 0;
 
     for (;;) {
@@ -329,8 +306,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         BSI_FOR_FILTER(BSI_DECL_K0)
         BSI_FOR_FILTER(BSI_DECL_K1)
         BSI_FOR_FILTER(BSI_DECL_K2)
-        u32 valid = 0u, F = 0u, alive = 0u;
+        u32 valid = 0u, F = 0u, alive = 0u, early = 0u;
         u32 st0 = 0, st1 = 0, st2 = 0;           // checkpoint time held by each slot
+        u32 yl_[BSI_N];                          // bit-sliced latch of the early matches' states
 
         if (active) {
             // ---- x_0 .. x_lp ----------------------------------------------------------------
@@ -378,9 +356,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
-                bsi_record(XS, m_, (J) - (ST), (ST), lam_s, c_s, y_s, sstride,       \
-                           (S) > 0 ? ck_s + ((S) - 1) * BSI_N * BSI_BLOCK : nullptr,  \
-                           (S) == 1 ? st0 : st1, (S), (S) > 0 || (ST) >= sched.first_final); \
+                bsi_record(XS, yl_, m_, (J) - (ST), (ST), lam_s, c_s, sstride, (S),  \
+                           (S) > 0 || (ST) >= sched.first_final);                    \
+                if (!((S) > 0 || (ST) >= sched.first_final)) early |= m_;            \
             }                                                                        \
         }                                                                            \
     }
@@ -531,18 +509,20 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         const u32 n_u = __popc(U);
         u64 base_f = bsi_reserve(&ctr->n_found, n_f);
         if (n_f) {
+            // state codes of the early matches: one transpose pass over the latch
+            u64 cw_[32][BSI_KW];
+            if (early) {
+#define BSI_LOAD_YL(i) a##i = yl_[i];
+                BSI_FOR_NODES(BSI_LOAD_YL)
+#undef BSI_LOAD_YL
+                BSI_UNPACK(cw_, a)
+            }
             u32 m = F;
             while (m) {
                 u32 l = __ffs(m) - 1;
                 m &= m - 1;
                 BsiFound r;
                 r.idx = DENSE ? (((word0 + w) << 5) + l) : in_queue[(w << 5) + l];
-#pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) {
-                    r.y[i] = y_s[(i * 32 + l) * sstride];
-                    r.key[i] = r.y[i];
-                    r.z[i] = y_s[((BSI_KW + i) * 32 + l) * sstride];
-                }
                 r.lam = lam_s[l * sstride];
                 r.c = c_s[l * sstride];
                 r.c0 = c_s[(32 + l) * sstride];
@@ -566,6 +546,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                         }
                         r.y[k] = y; r.key[k] = y; r.z[k] = z;
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BSI_KW; ++k) { r.y[k] = cw_[l][k]; r.key[k] = cw_[l][k]; r.z[k] = 0ull; }
                 }
                 found_q[base_f++] = r;
             }
