@@ -189,7 +189,7 @@ struct bsi_plan {
     bool mod_cached[6] = {false, false, false, false, false, false};   // owned by the module cache
     std::string unit_key[6];         // identifies a unit's source (module cache key)
     CUstream own_stream = nullptr, stream = nullptr;
-    CUfunction f_dense = nullptr, f_queue = nullptr, f_key = nullptr, f_mu = nullptr,
+    CUfunction f_dense = nullptr, f_queue = nullptr, f_mu = nullptr,
                f_resolve = nullptr, f_finish = nullptr,
                f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
     int n_sms = 0;
@@ -505,7 +505,6 @@ int load_plan(bsi_plan *p, int device) {
     if (p->m.mode == BSI_MODE_ATTRACT) {
         CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mods[1], "bsi_attract_dense"));
         CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
-        CU_CHECK(cuModuleGetFunction(&p->f_key, p->mods[3], "bsi_resolve_key"));
         CU_CHECK(cuModuleGetFunction(&p->f_resolve, p->mods[5], "bsi_resolve"));
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
@@ -520,8 +519,8 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_dense, p->block, p->main_smem));
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&b, p->f_queue, p->block, p->main_smem));
         p->main_blocks_per_sm = std::max(1, std::min(a, b));
-        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_key, p->block, 0));
-        p->key_blocks_per_sm = std::max(1, a);
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_finish, p->block, 0));
+        p->key_blocks_per_sm = std::max(1, std::min(a, 8));
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_mu, p->block, 0));
         p->mu_blocks_per_sm = std::max(1, a);
         p->table_log2 = p->opts.table_log2_slots ? p->opts.table_log2_slots : 20;
@@ -816,8 +815,8 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
             CU_CHECK(cuEventRecord(r0, p->stream));
             {
                 CUdeviceptr n_found_p = p->ctr.p + offsetof(Counters, n_found);
-                // all four resolution kernels are launched; the device picks the pair that fits the
-                // queue length (see bsi_template.cuh), the other two return at once
+                // all three resolution kernels are launched; the device picks the ones that fit
+                // the queue length (see bsi_template.cuh), the others return at once
                 uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
                 uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
                 void *args_k[] = {&p->found_q.p, &n_found_p, &few, &p->ctr.p};
@@ -825,7 +824,6 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
                                   &p->table_log2, &p->ctr.p};
                 unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
-                if ((rc = launch(p, p->f_key, grid_k, p->block, 0, args_k))) return rc;
                 if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
                 if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_k))) return rc;
                 if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;

@@ -610,25 +610,13 @@ bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final
 // minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
 // the cycle of found_q[32w + l] from y; walking more than lambda steps only revisits cycle
 // states, so all lanes of a word share the step count max lambda - 1.  lambda == 1: key = y.
-__device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64 w) {
+// in: cw_[32][KW] = on-cycle state codes of the valid lanes; out: their canonical keys, in place
+__device__ __forceinline__ void bsi_key_core(u64 (*cw_)[BSI_KW], u32 valid, u32 lam_max) {
+    if (lam_max <= 1u) return;                    // fixed points: the state is its own key
+    BSI_FOR_NODES(BSI_DECL_A)
+    BSI_FOR_NODES(BSI_DECL_B)
+    BSI_FOR_NODES(BSI_DECL_C)
     {
-        BSI_FOR_NODES(BSI_DECL_A)
-        BSI_FOR_NODES(BSI_DECL_B)
-        BSI_FOR_NODES(BSI_DECL_C)
-        u32 valid = 0u, lam_max = 0u;
-        u64 cw_[32][BSI_KW];
-#pragma unroll 1
-        for (u32 l = 0; l < 32; ++l) {
-            const u64 q = BSI_Q(w, l);
-            const bool in = q < n_found;
-#pragma unroll
-            for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = in ? found_q[q].y[i] : 0ull;
-            if (in) {
-                valid |= 1u << l;
-                lam_max = max(lam_max, found_q[q].lam);
-            }
-        }
-        if (lam_max <= 1u) return;
         BSI_PACK(a, cw_)
         BSI_FOR_NODES(BSI_COPY_CA)
         // lt_: lanes where X < c (decided at the most significant differing node)
@@ -657,12 +645,30 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
 #undef BSI_SEL_NODE
 #undef BSI_LEX_NODE
         BSI_UNPACK(cw_, c)
+    }
+}
+
+__device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64 w) {
+    u32 valid = 0u, lam_max = 0u;
+    u64 cw_[32][BSI_KW];
 #pragma unroll 1
-        for (u32 l = 0; l < 32; ++l) {
-            if ((valid >> l) & 1u) {
+    for (u32 l = 0; l < 32; ++l) {
+        const u64 q = BSI_Q(w, l);
+        const bool in = q < n_found;
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) found_q[BSI_Q(w, l)].key[i] = cw_[l][i];
-            }
+        for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = in ? found_q[q].y[i] : 0ull;
+        if (in) {
+            valid |= 1u << l;
+            lam_max = max(lam_max, found_q[q].lam);
+        }
+    }
+    if (lam_max <= 1u) return;
+    bsi_key_core(cw_, valid, lam_max);
+#pragma unroll 1
+    for (u32 l = 0; l < 32; ++l) {
+        if ((valid >> l) & 1u) {
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) found_q[BSI_Q(w, l)].key[i] = cw_[l][i];
         }
     }
 }
@@ -686,7 +692,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
-        u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u;
+        u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u, lam_max = 0u;
         // one pass over the 32 records of this word: every field that is needed later goes to
         // (thread-interleaved, hence coalesced) local arrays
         u64 cw_[32][BSI_KW], cz_[32][BSI_KW], cx_[32][BSI_KW];
@@ -717,13 +723,17 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
                 if (KEEP) {
                     keep->lam[l] = r.lam;
                     keep->c0[l] = r.c0;
+                    lam_max = max(lam_max, r.lam);
 #pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) keep->key[l][i] = r.key[i];
+                    for (int i = 0; i < BSI_KW; ++i) keep->key[l][i] = r.y[i];
                 }
             }
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
+        // (throughput path) the canonical keys, computed here: no separate pass over the records
+        if (KEEP) bsi_key_core(keep->key, valid, lam_max);
+        (void)lam_max;
         BSI_PACK(b, cw_)
         // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
 #define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
@@ -883,26 +893,15 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 }
 
 // Two ways to run the resolution, chosen ON THE DEVICE from the queue length (the host launches
-// all four kernels; the two that do not apply return at once):
-//  * many matched lanes (> few_words words): throughput matters -- bsi_resolve_key, then
-//    bsi_resolve_mu, which also finishes its lanes;
+// all three kernels; those that do not apply return at once):
+//  * many matched lanes (> few_words words): throughput matters -- bsi_resolve_mu reads every
+//    record once, walks for the keys (when some cycle is longer than 1) and for mu, and finishes
+//    its lanes;
 //  * few matched lanes: the walks are latency-bound chains that form the tail after every
 //    trajectory kernel -- bsi_resolve runs the mu walks and the key walks side by side (first
 //    and second half of its task range; tasks are handed out 32 at a time, so a warp is never
 //    split between the two), then bsi_resolve_finish aggregates.
 #if BSI_UNIT != 5
-extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve_key(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
-    const u64 n_found = *n_found_p;
-    if (((n_found + 31) >> 5) <= few_words) return;
-    const u64 n_words = BSI_QWORDS(n_found);
-    for (;;) {
-        const u64 w = bsi_grab_word(&ctr->next_word2);
-        if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w < n_words) bsi_key_word(found_q, n_found, w);
-    }
-}
-
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u64 max_attractor_l,
                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
