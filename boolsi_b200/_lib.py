@@ -31,7 +31,8 @@ EXPORTS = [
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
     'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
-    'bsi_attractor_states_batch', 'bsi_attract_schedule',
+    'bsi_attractor_states_batch', 'bsi_attract_schedule', 'bsi_attract_run_async',
+    'bsi_attract_run_finish',
 ]
 
 
@@ -120,6 +121,8 @@ def lib():
                                        C.POINTER(u64), C.c_char_p, u64]
         L.bsi_attract_run.argtypes = [p, u64, u64, u64, u64, C.POINTER(RunStats)]
         L.bsi_attract_table_clear.argtypes = [p]
+        L.bsi_attract_run_async.argtypes = [p, u64, u64, u64, u64]
+        L.bsi_attract_run_finish.argtypes = [p, C.POINTER(RunStats)]
         L.bsi_attract_table_count.argtypes = [p, C.POINTER(u64)]
         L.bsi_attract_table_read.argtypes = [p, p, u64, C.POINTER(u64)]
         L.bsi_attract_table_export_device.argtypes = [p, p, u64, C.POINTER(u64)]
@@ -326,6 +329,16 @@ class Plan:
         st = RunStats()
         check(lib().bsi_attract_run(self._h, int(idx_begin), int(idx_end), cap(max_t),
                                     cap(max_attractor_l), C.byref(st)))
+        return st.as_dict()
+
+    def attract_run_async(self, idx_begin, idx_end, max_t=inf, max_attractor_l=inf):
+        """Enqueue the run on the plan's stream; collect with `attract_run_finish`."""
+        check(lib().bsi_attract_run_async(self._h, int(idx_begin), int(idx_end), cap(max_t),
+                                          cap(max_attractor_l)))
+
+    def attract_run_finish(self):
+        st = RunStats()
+        check(lib().bsi_attract_run_finish(self._h, C.byref(st)))
         return st.as_dict()
 
     def table_clear(self):

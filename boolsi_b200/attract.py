@@ -57,15 +57,19 @@ class AttractEngine:
         Afterwards every rank holds the complete table on its device.
         :return: run stats of this rank (`steps` etc.) + job totals in `self.totals`"""
         self.plan.table_clear()
-        st = self.plan.attract_run(self.lo, self.hi, max_t, max_attractor_l)
-        totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
-        if self.world > 1:
-            totals = self._merge_over_ranks(st)
-            st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
-        self.totals = totals
+        if self.world == 1:
+            st = self.plan.attract_run(self.lo, self.hi, max_t, max_attractor_l)
+            self.totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
+            return st
+        # kernels, table export and the collective are enqueued back to back; the first host
+        # synchronisation is the read of the gathered headers
+        self.plan.attract_run_async(self.lo, self.hi, max_t, max_attractor_l)
+        self.totals = self._merge_over_ranks()
+        st = self.plan.attract_run_finish()
+        st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
         return st
 
-    def _merge_over_ranks(self, st):
+    def _merge_over_ranks(self):
         from .sharding import exchange_tables
         if self._gather is None:
             self._gather = {}

@@ -200,6 +200,12 @@ struct bsi_plan {
     std::vector<CUevent> events;
     size_t events_used = 0;
     uint64_t launches = 0;
+    // a run enqueued by bsi_attract_run_async and not yet collected by bsi_attract_run_finish
+    bool pending = false, pending_trivial = false;
+    bsi_run_stats pending_stats{};
+    uint64_t pending_launches0 = 0;
+    CUevent pending_e0 = nullptr, pending_e1 = nullptr;
+    std::vector<std::pair<CUevent, CUevent>> pending_main, pending_resolve;
 };
 
 namespace {
@@ -735,19 +741,34 @@ int bsi_compile_only(const bsi_network_desc *network, const bsi_space_desc *spac
 }
 
 // ---- attract ------------------------------------------------------------------------------------
-int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
-                    uint64_t max_attractor_l, bsi_run_stats *stats) {
+static int attract_collect(bsi_plan *p, bsi_run_stats *stats);
+
+static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                           uint64_t max_attractor_l, bsi_run_stats *stats, bool async) {
     int rc = need_device(p, BSI_MODE_ATTRACT);
     if (rc) return rc;
+    if (p->pending) return fail(BSI_E_ARG, "a run enqueued by bsi_attract_run_async has not been collected (bsi_attract_run_finish)");
     if (idx_begin > idx_end || idx_end > p->m.n_problems) return fail(BSI_E_ARG, "bad index range");
     bsi_run_stats st{};
     st.n_problems = idx_end - idx_begin;
     const uint64_t lp = p->m.lp_origin;
-    if (st.n_problems == 0) { if (stats) *stats = st; return BSI_OK; }
-    if (max_t <= lp) {
-        // model.py:201: the loop body never runs; every problem stops at t = lp with no attractor
+    if (st.n_problems == 0 || max_t <= lp) {
+        // nothing to launch.  max_t <= lp: model.py:201, the loop body never runs; every problem
+        // stops at t = lp with no attractor.  The device counters still get the totals (the
+        // exchange payload header is written from them).
         st.n_without = st.n_problems;
         st.steps = st.n_problems * lp;
+        CtxGuard g0(p);
+        Counters h{};
+        h.n_without = st.n_without;
+        h.steps = st.steps;
+        CU_CHECK(cuMemcpyHtoDAsync(p->ctr.p, &h, sizeof h, p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+        if (async) {
+            p->pending = true;
+            p->pending_trivial = true;
+            p->pending_stats = st;
+        }
         if (stats) *stats = st;
         return BSI_OK;
     }
@@ -848,26 +869,65 @@ int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t 
         b = e;
     }
     CU_CHECK(cuEventRecord(tm.e1, p->stream));
+    p->pending = true;
+    p->pending_stats = st;
+    p->pending_launches0 = launches0;
+    p->pending_e0 = tm.e0;
+    p->pending_e1 = tm.e1;
+    p->pending_main = tm.main;
+    p->pending_resolve = tm.resolve;
+    if (async) return BSI_OK;
+    return attract_collect(p, stats);
+}
+
+// waits for an enqueued run, reads its counters and timings, checks the invariants
+static int attract_collect(bsi_plan *p, bsi_run_stats *stats) {
+    int rc;
+    p->pending = false;
+    bsi_run_stats st = p->pending_stats;
+    if (p->pending_trivial) {
+        p->pending_trivial = false;
+        if (stats) *stats = st;
+        return BSI_OK;
+    }
     Counters c;
     if ((rc = read_counters(p, &c))) return rc;
-    CU_CHECK(cuEventSynchronize(tm.e1));
+    CU_CHECK(cuEventSynchronize(p->pending_e1));
     if (c.table_full) return fail(BSI_E_CAPACITY, "attractor table overflow (raise table_log2_slots)");
     if (c.internal_error) return fail(BSI_E_CUDA, "internal invariant failed in bsi_resolve_mu");
     st.n_found = c.n_accepted;
     st.n_without = c.n_without;
     st.steps = c.steps;
     st.device_steps = c.device_steps;
-    st.launches = p->launches - launches0;
+    st.launches = p->launches - p->pending_launches0;
     for (int k = 0; k < 4; ++k) st.reserved[k] = c.pad[k];      // debug_stats counters
-    if ((rc = elapsed(tm.e0, tm.e1, &st.ms_total))) return rc;
-    for (auto &pr : tm.main) if ((rc = elapsed(pr.first, pr.second, &st.ms_main))) return rc;
-    for (auto &pr : tm.resolve) if ((rc = elapsed(pr.first, pr.second, &st.ms_resolve))) return rc;
+    if ((rc = elapsed(p->pending_e0, p->pending_e1, &st.ms_total))) return rc;
+    for (auto &pr : p->pending_main) if ((rc = elapsed(pr.first, pr.second, &st.ms_main))) return rc;
+    for (auto &pr : p->pending_resolve) if ((rc = elapsed(pr.first, pr.second, &st.ms_resolve))) return rc;
     if (st.n_found + st.n_without != st.n_problems)
         return fail(BSI_E_CUDA, "internal: %llu found + %llu without != %llu problems",
                     (unsigned long long)st.n_found, (unsigned long long)st.n_without,
                     (unsigned long long)st.n_problems);
     if (stats) *stats = st;
     return BSI_OK;
+}
+
+int bsi_attract_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                    uint64_t max_attractor_l, bsi_run_stats *stats) {
+    return attract_enqueue(p, idx_begin, idx_end, max_t, max_attractor_l, stats, false);
+}
+
+int bsi_attract_run_async(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                          uint64_t max_attractor_l) {
+    return attract_enqueue(p, idx_begin, idx_end, max_t, max_attractor_l, nullptr, true);
+}
+
+int bsi_attract_run_finish(bsi_plan *p, bsi_run_stats *stats) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (!p->pending) return fail(BSI_E_ARG, "no run is pending");
+    CtxGuard g(p);
+    return attract_collect(p, stats);
 }
 
 int bsi_attract_table_clear(bsi_plan *p) {

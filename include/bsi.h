@@ -204,6 +204,14 @@ int bsi_attract_schedule(uint64_t horizon, uint32_t *ck_time, uint32_t *ck_slot,
 /* Runs problems [idx_begin, idx_end) and ACCUMULATES into the plan's device attractor table. */
 int bsi_attract_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
                     uint64_t max_attractor_l, bsi_run_stats *stats);
+/* The same, without waiting: everything is enqueued on the plan's stream and the call returns (when
+ * the run needs more than one detection round -- max_t beyond the first horizon -- the host must
+ * read queue lengths between rounds and the call only returns after the last round is enqueued).
+ * Table exports / merges / the next run may be enqueued behind it; bsi_attract_run_finish waits,
+ * returns the statistics and reports errors.  One run may be pending per plan. */
+int bsi_attract_run_async(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                          uint64_t max_attractor_l);
+int bsi_attract_run_finish(bsi_plan *plan, bsi_run_stats *stats);
 int bsi_attract_table_clear(bsi_plan *plan);
 int bsi_attract_table_count(bsi_plan *plan, uint64_t *n);
 /* Copy the table to HOST memory (unsorted). */

@@ -193,8 +193,16 @@ def test_two_shards_export_payload_and_merge_equal_the_whole():
     stats = []
     for r, (plan, buf) in enumerate(zip(plans, bufs)):
         lo, hi = shard_range(pk.n_problems, r, 2)
-        stats.append(plan.attract_run(lo, hi, a['max_t'], a['max_attractor_l']))
-        plan.table_export_payload(buf.data_ptr(), buf.shape[0])
+        if r == 0:
+            stats.append(plan.attract_run(lo, hi, a['max_t'], a['max_attractor_l']))
+            plan.table_export_payload(buf.data_ptr(), buf.shape[0])
+        else:
+            # the asynchronous form: run and export are enqueued, statistics collected afterwards
+            plan.attract_run_async(lo, hi, a['max_t'], a['max_attractor_l'])
+            plan.table_export_payload(buf.data_ptr(), buf.shape[0])
+            with pytest.raises(_lib.BsiError):
+                plan.attract_run_async(lo, hi, a['max_t'], a['max_attractor_l'])    # one pending run per plan
+            stats.append(plan.attract_run_finish())
     torch.cuda.synchronize()
     headers = [b[0].cpu().tolist() for b in bufs]
     for h, st, plan in zip(headers, stats, plans):
