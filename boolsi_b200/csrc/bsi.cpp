@@ -691,7 +691,10 @@ int bsi_plan_key_words(const bsi_plan *p, uint32_t *kw) {
 
 int bsi_plan_set_stream(bsi_plan *p, void *cuda_stream) {
     if (!p) return fail(BSI_E_ARG, "null plan");
-    p->stream = cuda_stream ? (CUstream)cuda_stream : p->own_stream;
+    // NULL is the CUDA default (legacy) stream -- what torch.cuda.current_stream().cuda_stream is
+    // when no stream context is active; ((void *)-1) goes back to the plan's own stream
+    if (cuda_stream == (void *)-1) p->stream = p->own_stream;
+    else p->stream = cuda_stream ? (CUstream)cuda_stream : CU_STREAM_LEGACY;
     return BSI_OK;
 }
 

@@ -172,7 +172,9 @@ int bsi_plan_create_offline(const bsi_network_desc *network, const bsi_space_des
 void bsi_plan_destroy(bsi_plan *plan);
 int bsi_plan_n_problems(const bsi_plan *plan, uint64_t *n);   /* 'total combination count' */
 int bsi_plan_key_words(const bsi_plan *plan, uint32_t *kw);
-int bsi_plan_set_stream(bsi_plan *plan, void *cuda_stream);   /* cudaStream_t; NULL = default */
+/* A plan starts on its own non-blocking stream.  cuda_stream: a cudaStream_t / CUstream handle;
+ * NULL = the CUDA default (legacy) stream; (void *)-1 = back to the plan's own stream. */
+int bsi_plan_set_stream(bsi_plan *plan, void *cuda_stream);
 /* Generated CUDA source / build log (NUL-terminated, owned by the plan). */
 const char *bsi_plan_source(const bsi_plan *plan);
 const char *bsi_plan_build_log(const bsi_plan *plan);
