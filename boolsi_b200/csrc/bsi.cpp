@@ -381,8 +381,10 @@ UnitResult compile_unit(std::string src) {
         out.error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
         return out;
     }
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
-    r = nvrtcCompileProgram(prog, 4, opts);
+    // (#550 "set but never used": generated per-node temporaries of rules that do not use them)
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device",
+                          "--diag-suppress=550"};
+    r = nvrtcCompileProgram(prog, 5, opts);
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);
     out.log.assign(log_size ? log_size : 1, '\0');
