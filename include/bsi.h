@@ -110,13 +110,13 @@ typedef struct bsi_target_desc {
 
 /* Tuning knobs; zero-initialise for defaults. */
 typedef struct bsi_plan_opts {
-    uint32_t first_horizon;    /* attract: horizon of the first detection round; 0 = auto */
+    uint32_t first_horizon;    /* attract: horizon of the first detection round; 0 = auto (1024) */
     uint32_t filter_nodes;     /* attract: #nodes in the cheap pre-compare; 0 = auto (12) */
     uint32_t table_log2_slots; /* attract: device hash table size; 0 = auto (20) */
     uint32_t chunk_log2;       /* problems per launch wave; 0 = auto (26) */
     uint32_t keep_source;      /* unused: the generated source is always kept */
     uint32_t block_threads;    /* threads per block of the trajectory kernels; 0 = auto (64) */
-    uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto       */
+    uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto (1) */
     uint32_t debug_stats;      /* 1: count filter events (stats->reserved[0] = stage-2 filter entries,
                                   [1] = full compares); costs atomics, for tuning only */
     uint32_t resolve_few_words;/* attract: queue length (words of 32 matched lanes) up to which the
@@ -142,7 +142,7 @@ typedef struct bsi_run_stats {
                                   when a trajectory closes its cycle before max_t without a hit) */
     uint64_t device_steps;     /* 32-lane word-steps actually executed by the main kernels */
     uint64_t launches;         /* kernels launched by this call */
-    uint64_t rounds;           /* attract: detection rounds (horizon doublings + 1) */
+    uint64_t rounds;           /* attract / target: detection rounds over all chunks */
     double ms_total;           /* device time of the call (CUDA events on the plan's stream) */
     double ms_main;            /* device time of the dominant (trajectory) kernels */
     double ms_resolve;         /* device time of the per-attractor resolution kernels */
