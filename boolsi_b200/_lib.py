@@ -65,7 +65,8 @@ class PlanOpts(C.Structure):
                 ('table_log2_slots', C.c_uint32), ('chunk_log2', C.c_uint32),
                 ('keep_source', C.c_uint32), ('block_threads', C.c_uint32),
                 ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
-                ('resolve_few_words', C.c_uint32), ('reserved', C.c_uint32 * 7)]
+                ('resolve_few_words', C.c_uint32), ('no_early_words', C.c_uint32),
+                ('reserved', C.c_uint32 * 6)]
 
 
 class RunStats(C.Structure):

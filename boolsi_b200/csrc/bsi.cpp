@@ -110,11 +110,12 @@ const char *cu_errstr(CUresult r) {
 
 // mirrors of the device structs in bsi_template.cuh
 struct Counters {
-    uint64_t next_word, next_word2, next_word3, n_found, n_retry;
+    uint64_t next_word, next_word2, next_word3, n_found, n_retry, n_early, next_word4;
     uint64_t n_without, n_accepted, steps, device_steps, table_full, n_hits, internal_error;
-    uint64_t pad[4];
+    uint64_t pad[2];
+    uint64_t dbg[4];
 };
-constexpr size_t kPerRoundBytes = 5 * sizeof(uint64_t);
+constexpr size_t kPerRoundBytes = 7 * sizeof(uint64_t);
 constexpr int kMaxCk = 72;
 struct Sched {
     uint32_t n_ck, end, first_final, pad;
@@ -180,23 +181,23 @@ struct bsi_plan {
     bsi::GenInfo info;
     bsi_plan_opts opts{};
     std::string source, log;
-    std::vector<char> cubins[6];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 resolve, 4 the rest)
+    std::vector<char> cubins[7];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 + 6 resolve, 4 the rest)
     int block = 64;
     int device = -1;           // -1: compile-only plan
     CUdevice dev = 0;
     CUcontext ctx = nullptr;
-    CUmodule mods[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool mod_cached[6] = {false, false, false, false, false, false};   // owned by the module cache
-    std::string unit_key[6];         // identifies a unit's source (module cache key)
+    CUmodule mods[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool mod_cached[7] = {false, false, false, false, false, false, false};   // owned by the module cache
+    std::string unit_key[7];         // identifies a unit's source (module cache key)
     CUstream own_stream = nullptr, stream = nullptr;
-    CUfunction f_dense = nullptr, f_queue = nullptr, f_mu = nullptr,
+    CUfunction f_dense = nullptr, f_queue = nullptr, f_mu = nullptr, f_early = nullptr,
                f_resolve = nullptr, f_finish = nullptr,
                f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
     int n_sms = 0;
     int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
     size_t main_smem = 0;
     uint32_t table_log2 = 20;
-    DevBuf ctr, table, found_q, retry_q[2], scratch, misc, misc2, misc3;
+    DevBuf ctr, table, found_q, retry_q[2], scratch, early_q, misc, misc2, misc3;
     std::vector<CUevent> events;
     size_t events_used = 0;
     uint64_t launches = 0;
@@ -450,7 +451,7 @@ int compile_plan(bsi_plan *p) {
     // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
     // thread-safe across programs): the two trajectory kernels dominate the compile time.
     std::vector<int> units;
-    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 5, 4}; else units = {4};
+    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 5, 6, 4}; else units = {4};
     std::vector<std::future<UnitResult>> jobs;
     for (int u : units) {
         std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
@@ -490,7 +491,7 @@ int load_plan(bsi_plan *p, int device) {
     {
         static std::map<std::string, CUmodule> loaded;
         std::lock_guard<std::mutex> lk(g_dev_mu);
-        for (int u = 1; u <= 5; ++u) {
+        for (int u = 1; u <= 6; ++u) {
             if (p->cubins[u].empty()) continue;
             const std::string key = std::to_string(device) + "/" + p->unit_key[u];
             auto it = loaded.find(key);
@@ -515,6 +516,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
         CU_CHECK(cuModuleGetFunction(&p->f_resolve, p->mods[5], "bsi_resolve"));
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
+        CU_CHECK(cuModuleGetFunction(&p->f_early, p->mods[6], "bsi_resolve_early"));
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
@@ -633,12 +635,12 @@ void bsi_plan_destroy(bsi_plan *p) {
             CtxGuard g(p);
             if (p->stream) cu().p_cuStreamSynchronize(p->stream);
             for (DevBuf *b : {&p->ctr, &p->table, &p->found_q, &p->retry_q[0], &p->retry_q[1], &p->scratch,
-                              &p->misc, &p->misc2, &p->misc3})
+                              &p->early_q, &p->misc, &p->misc2, &p->misc3})
                 give_back(p->device, *b);
             tm.lap("destroy: buffers");
             for (CUevent e : p->events) cu().p_cuEventDestroy(e);
             if (p->own_stream) cu().p_cuStreamDestroy(p->own_stream);
-            for (int u = 0; u < 6; ++u) if (p->mods[u] && !p->mod_cached[u]) cu().p_cuModuleUnload(p->mods[u]);
+            for (int u = 0; u < 7; ++u) if (p->mods[u] && !p->mod_cached[u]) cu().p_cuModuleUnload(p->mods[u]);
             tm.lap("destroy: module/stream");
         }
     }
@@ -823,8 +825,14 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
             CUdeviceptr retry_out = final_round ? 0 : p->retry_q[which].p;
             if (dense) {
                 uint64_t word0 = b >> 5, n_words = ((e + 31) >> 5) - word0;
+                // early-word queue: one entry per word at most
+                uint64_t early_cap = p->opts.no_early_words ? 0 : n_words;
+                if (early_cap &&
+                    (rc = ensure(p, p->early_q, early_cap * (8 + 4 + 32 * 8 + 4 * (size_t)p->m.n) + 256)))
+                    return rc;
+                CUdeviceptr early_p = early_cap ? p->early_q.p : 0;
                 void *args[] = {&word0, &n_words, &b, &e, &sched, (void *)&final_round, &stop_t,
-                                &p->found_q.p, &retry_out, &p->scratch.p, &p->ctr.p};
+                                &p->found_q.p, &retry_out, &p->scratch.p, &early_p, &early_cap, &p->ctr.p};
                 unsigned grid = (unsigned)std::min<uint64_t>(main_grid, (n_words + p->block - 1) / p->block);
                 if ((rc = launch(p, p->f_dense, grid, p->block, p->main_smem, args))) return rc;
             } else {
@@ -850,6 +858,13 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                                   &p->table_log2, &p->ctr.p};
                 unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
+                if (dense && !p->opts.no_early_words) {
+                    uint64_t word0 = b >> 5, early_cap = ((e + 31) >> 5) - word0;
+                    CUdeviceptr n_early_p = p->ctr.p + offsetof(Counters, n_early);
+                    void *args_e[] = {&p->early_q.p, &early_cap, &n_early_p, &t_rel, &cap_l, &stop_cap,
+                                      &p->table.p, &p->table_log2, &p->ctr.p};
+                    if ((rc = launch(p, p->f_early, grid_m, p->block, 0, args_e))) return rc;
+                }
                 if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
                 if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_k))) return rc;
                 if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;
@@ -905,7 +920,7 @@ static int attract_collect(bsi_plan *p, bsi_run_stats *stats) {
     st.steps = c.steps;
     st.device_steps = c.device_steps;
     st.launches = p->launches - p->pending_launches0;
-    for (int k = 0; k < 4; ++k) st.reserved[k] = c.pad[k];      // debug_stats counters
+    for (int k = 0; k < 4; ++k) st.reserved[k] = c.dbg[k];      // debug_stats counters
     if ((rc = elapsed(p->pending_e0, p->pending_e1, &st.ms_total))) return rc;
     for (auto &pr : p->pending_main) if ((rc = elapsed(pr.first, pr.second, &st.ms_main))) return rc;
     for (auto &pr : p->pending_resolve) if ((rc = elapsed(pr.first, pr.second, &st.ms_resolve))) return rc;

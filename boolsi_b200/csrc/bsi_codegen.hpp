@@ -470,6 +470,8 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
             o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
         for (int i = 0; i < n; ++i) o << " (P)[" << i << " * (S)] = X##" << i << ";";
+        o << " }\n#define BSI_LOAD_MEM(X, P, S) {";
+        for (int i = 0; i < n; ++i) o << " X##" << i << " = (P)[" << i << " * (S)];";
         o << " }\n#define BSI_DUMP(X, A) {";
         for (int i = 0; i < n; ++i) o << " (A)[" << i << "] = X##" << i << ";";
         o << " }\n";

@@ -64,6 +64,8 @@ struct BsiCounters {
     u64 next_word3;     // work counter of bsi_resolve_mu
     u64 n_found;        // entries in the found queue (target: closed queue)
     u64 n_retry;        // entries in the retry queue
+    u64 n_early;        // entries in the early-word queue
+    u64 next_word4;     // work counter of bsi_resolve_early
     // accumulated over a run
     u64 n_without;      // lanes proven to have no attractor within the caps
     u64 n_accepted;     // lanes whose attractor went into the table
@@ -72,7 +74,8 @@ struct BsiCounters {
     u64 table_full;     // set when the attractor table overflowed
     u64 n_hits;         // target: number of hits
     u64 internal_error; // set when an invariant of the resolution kernels failed
-    u64 pad[4];
+    u64 pad[2];
+    u64 dbg[4];         // debug_stats counters
 };
 
 struct BsiSched {       // checkpoint schedule of one detection round (times relative to lp)
@@ -94,6 +97,26 @@ struct BsiFound {       // one lane that matched a checkpoint
     u32 c0;             // a time < mu: the previous final checkpoint, or 0 (then x_0 comes from idx)
     u32 pad;
 };
+
+// Early-word queue (dense rounds only): a word whose lanes matched EARLY checkpoints hands them
+// over bit-sliced -- no per-lane records, no transposes.  Structure of arrays over the entry e:
+//   u64 word[cap]; u32 mask[cap]; u64 lamc[32][cap] (lambda | c << 32); u32 y[N][cap] (the latch)
+struct BsiEarlyQ {
+    u64 *word;
+    u32 *mask;
+    u64 *lamc;
+    u32 *y;
+    u64 cap;
+};
+__device__ __forceinline__ BsiEarlyQ bsi_early_view(void *base, u64 cap) {
+    BsiEarlyQ q;
+    q.cap = cap;
+    q.word = (u64 *)base;
+    q.lamc = q.word + cap;
+    q.mask = (u32 *)(q.lamc + 32ull * cap);
+    q.y = q.mask + cap;
+    return q;
+}
 
 struct BsiSlot {
     u64 key[BSI_KW];
@@ -287,7 +310,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                                               const u64 *__restrict__ in_queue, u64 n_in,
                                               const BsiSched &sched, int final_round, u64 stop_t,
                                               BsiFound *found_q, u64 *retry_q, u32 *scratch,
-                                              BsiCounters *ctr) {
+                                              void *early_base, u64 early_cap, BsiCounters *ctr) {
     const u32 tid = threadIdx.x;
     u32 *const ck_s = (u32 *)bsi_smem + tid;                          // checkpoints [slot][node][BLOCK]
     const u64 sstride = (u64)gridDim.x * BSI_BLOCK;
@@ -363,7 +386,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         }                                                                            \
     }
 #if BSI_STATS
-#define BSI_COUNT(k) atomicAdd(&ctr->pad[k], 1ull);
+#define BSI_COUNT(k) atomicAdd(&ctr->dbg[k], 1ull);
 #else
 #define BSI_COUNT(k)
 #endif
@@ -503,9 +526,30 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #undef BSI_STAGE2
         }
 
-        // ---- results: matched lanes -> found queue, others -> retry queue / "no attractor" ----
+        // ---- results ------------------------------------------------------------------------------
+        const u32 matched = F;
+        // early matches of a dense word -> early-word queue, bit-sliced as they are
+        if (DENSE && early_cap) {
+            const u64 e = bsi_reserve(&ctr->n_early, early ? 1u : 0u);
+            if (early) {
+                const BsiEarlyQ q = bsi_early_view(early_base, early_cap);
+                q.word[e] = word0 + w;
+                q.mask[e] = early;
+                u32 m = early;
+                while (m) {
+                    const u32 l = __ffs(m) - 1;
+                    m &= m - 1;
+                    q.lamc[l * early_cap + e] = (u64)lam_s[l * sstride] | ((u64)c_s[l * sstride] << 32);
+                }
+#pragma unroll 8
+                for (int i = 0; i < BSI_N; ++i) q.y[i * early_cap + e] = yl_[i];
+                F &= ~early;
+                early = 0u;
+            }
+        }
+        // other matched lanes -> found queue, open lanes -> retry queue / "no attractor"
         const u32 n_f = __popc(F);
-        const u32 U = valid & ~F;
+        const u32 U = valid & ~matched;
         const u32 n_u = __popc(U);
         u64 base_f = bsi_reserve(&ctr->n_found, n_f);
         if (n_f) {
@@ -573,14 +617,14 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 
 // The translation unit is compiled once per BSI_UNIT (in parallel, see bsi.cpp): 1 = dense
 // trajectory kernel, 2 = queue trajectory kernel, 3 = resolution kernels, 4 = everything else;
-// 5 = the latency-oriented resolution kernels; 0 = all of it (the ahead-of-time nvcc build check).
+// 5 = the latency-oriented resolution kernels, 6 = the early-word resolution kernel; 0 = all of it (the ahead-of-time nvcc build check).
 #if BSI_UNIT == 0 || BSI_UNIT == 1
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
 bsi_attract_dense(u64 word0, u64 n_words, u64 idx_begin, u64 idx_end, const BsiSched sched,
                   int final_round, u64 stop_t, BsiFound *found_q, u64 *retry_q, u32 *scratch,
-                  BsiCounters *ctr) {
+                  void *early_q, u64 early_cap, BsiCounters *ctr) {
     bsi_main_body<true>(word0, n_words, idx_begin, idx_end, nullptr, 0, sched, final_round, stop_t,
-                        found_q, retry_q, scratch, ctr);
+                        found_q, retry_q, scratch, early_q, early_cap, ctr);
 }
 #endif
 
@@ -589,14 +633,14 @@ extern "C" __global__ void __launch_bounds__(BSI_BLOCK, BSI_MIN_BLOCKS)
 bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final_round, u64 stop_t,
                   BsiFound *found_q, u64 *retry_q, u32 *scratch, BsiCounters *ctr) {
     bsi_main_body<false>(0, (n_in + 31) >> 5, 0, 0, in_queue, n_in, sched, final_round, stop_t,
-                         found_q, retry_q, scratch, ctr);
+                         found_q, retry_q, scratch, nullptr, 0, ctr);
 }
 #endif
 
 // ---------------------------------------------------------------------------------------------
 // attract: exact resolution of the matched lanes
 // ---------------------------------------------------------------------------------------------
-#if BSI_UNIT == 0 || BSI_UNIT == 3 || BSI_UNIT == 5
+#if BSI_UNIT == 0 || BSI_UNIT == 3 || BSI_UNIT == 5 || BSI_UNIT == 6
 
 // Which records of the found queue form "word" w of the resolution kernels: words come in groups
 // of 32 (one warp), a group owns 1024 consecutive records, and lane l of the group's t-th word is
@@ -684,9 +728,12 @@ struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it
     u32 lam[32], c0[32];
 };
 
-template <bool WRITE_PAD, bool KEEP>
+// EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in eq.y, all
+// starting from the dense problem-index word eq.word[w], c0 = 0); otherwise word w of found_q.
+template <bool WRITE_PAD, bool KEEP, bool EARLY>
 __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
-                                            BsiCounters *ctr, BsiKeep *keep) {
+                                            BsiCounters *ctr, BsiKeep *keep, const BsiEarlyQ &eq,
+                                            u32 &valid_out) {
     const u32 tid = threadIdx.x;
     {
         BSI_FOR_NODES(BSI_DECL_A)
@@ -695,9 +742,26 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u, lam_max = 0u;
         // one pass over the 32 records of this word: every field that is needed later goes to
         // (thread-interleaved, hence coalesced) local arrays
-        u64 cw_[32][BSI_KW], cz_[32][BSI_KW], cx_[32][BSI_KW];
+        u64 cw_[EARLY ? 1 : 32][BSI_KW], cz_[EARLY ? 1 : 32][BSI_KW], cx_[EARLY ? 1 : 32][BSI_KW];
+        if (EARLY) {
+            valid = eq.mask[w];
+            from_idx = valid;
 #pragma unroll 1
-        for (u32 l = 0; l < 32; ++l) {
+            for (u32 l = 0; l < 32; ++l) {
+                if (!((valid >> l) & 1u)) continue;
+                const u64 lc = eq.lamc[l * eq.cap + w];
+                const u32 lam = (u32)lc, c = (u32)(lc >> 32);
+                const u32 adv = (lam - c % lam) % lam;
+                aux_s[l * BSI_BLOCK + tid] = adv;
+                adv_max = max(adv_max, adv);
+                c_max = max(c_max, c);
+                lam_max = max(lam_max, lam);
+                keep->lam[l] = lam;
+                keep->c0[l] = 0u;
+            }
+        }
+#pragma unroll 1
+        for (u32 l = 0; !EARLY && l < 32; ++l) {
             const u64 q = BSI_Q(w, l);
             u64 x_[BSI_KW];
 #pragma unroll
@@ -731,10 +795,19 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
-        // (throughput path) the canonical keys, computed here: no separate pass over the records
+        if (EARLY) {
+            BSI_LOAD_MEM(b, (eq.y + w), eq.cap)
+            BSI_UNPACK(keep->key, b)                 // the states as codes: keys of the fixed points
+        }
+        // (throughput paths) the canonical keys, computed here: no separate pass over the records
         if (KEEP) bsi_key_core(keep->key, valid, lam_max);
         (void)lam_max;
-        BSI_PACK(b, cw_)
+        valid_out = valid;
+        if (EARLY) {
+            BSI_LOAD_MEM(b, (eq.y + w), eq.cap)      // (again: the key walk needed the registers)
+        } else {
+            BSI_PACK(b, cw_)
+        }
         // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
 #define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
         {
@@ -763,15 +836,21 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #define BSI_MASK_A(i) a##i &= from_idx;
 #define BSI_OR_AB(i) a##i |= b##i;
             BSI_FOR_NODES(BSI_COPY_CB)
-            BSI_FOR_NODES(BSI_ZERO_A)
-            if (from_idx) {
-                BSI_PACK(a, cx_)
+            if (EARLY) {
+                const u64 W_ = eq.word[w];
+                BSI_INIT_DENSE(a, W_)
                 BSI_PREFIX(BSI_LP_ORIGIN)
-                BSI_FOR_NODES(BSI_MASK_A)
-            }
-            if (valid & ~from_idx) {
-                BSI_PACK(b, cz_)
-                BSI_FOR_NODES(BSI_OR_AB)
+            } else {
+                BSI_FOR_NODES(BSI_ZERO_A)
+                if (from_idx) {
+                    BSI_PACK(a, cx_)
+                    BSI_PREFIX(BSI_LP_ORIGIN)
+                    BSI_FOR_NODES(BSI_MASK_A)
+                }
+                if (valid & ~from_idx) {
+                    BSI_PACK(b, cz_)
+                    BSI_FOR_NODES(BSI_OR_AB)
+                }
             }
             BSI_FOR_NODES(BSI_COPY_BC)
 #undef BSI_OR_AB
@@ -829,14 +908,12 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                                                 u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
                                                 u32 log2_slots, BsiCounters *ctr, u64 &steps,
                                                 u64 &n_acc, u64 &n_rej, const u32 *aux_s,
-                                                BsiKeep *keep) {
+                                                BsiKeep *keep, u32 lanes) {
     {
         u32 todo = 0u;
         if (FROM_KEEP) {
             // same kernel as the mu walk: keys / lambda / c0 were kept, mu - c0 is in aux_s
-#pragma unroll 1
-            for (u32 l = 0; l < 32; ++l)
-                if (BSI_Q(w, l) < n_found) todo |= 1u << l;
+            todo = lanes;
         } else {
             // another kernel: one pass over the records; mu itself is in the pad field
 #pragma unroll 1
@@ -901,7 +978,7 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 //    trajectory kernel -- bsi_resolve runs the mu walks and the key walks side by side (first
 //    and second half of its task range; tasks are handed out 32 at a time, so a warp is never
 //    split between the two), then bsi_resolve_finish aggregates.
-#if BSI_UNIT != 5
+#if BSI_UNIT != 5 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u64 max_attractor_l,
                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
@@ -911,13 +988,15 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
     const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
     BsiKeep keep;
+    const BsiEarlyQ no_early = bsi_early_view(nullptr, 0);
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
         if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
-        bsi_mu_word<false, true>(found_q, n_found, w, aux_s, ctr, &keep);
+        u32 lanes = 0u;
+        bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, lanes);
         bsi_finish_word<true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
-                              ctr, steps, n_acc, n_rej, aux_s, &keep);
+                              ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
@@ -925,7 +1004,33 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
 }
 
 #endif  // BSI_UNIT != 5
-#if BSI_UNIT != 3
+#if BSI_UNIT == 0 || BSI_UNIT == 6
+// The early-word queue of a dense round: keys, mu and aggregation of lanes that matched an early
+// checkpoint, straight from their bit-sliced states (no records, one transpose pass per word).
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, u64 T, u64 max_attractor_l,
+                  u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+    __shared__ u32 aux_s[32 * BSI_BLOCK];
+    const u64 n_early = *n_early_p;
+    if (n_early == 0) return;
+    const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
+    u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiKeep keep;
+    for (;;) {
+        const u64 e = bsi_grab_word(&ctr->next_word4);
+        if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
+        if (e >= n_early) continue;
+        u32 lanes = 0u;
+        bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, lanes);
+        bsi_finish_word<true>(nullptr, 0, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
+                              steps, n_acc, n_rej, aux_s, &keep, lanes);
+    }
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
+    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
+}
+#endif  // BSI_UNIT 6
+#if BSI_UNIT != 3 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
@@ -936,7 +1041,11 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters 
         const u64 t = bsi_grab_word(&ctr->next_word2);
         if (__all_sync(0xFFFFFFFFu, t >= 2 * w32)) break;
         if (t < w32) {
-            if (BSI_Q(t, 0) < n_found) bsi_mu_word<true, false>(found_q, n_found, t, aux_s, ctr, nullptr);
+            if (BSI_Q(t, 0) < n_found) {
+                u32 lanes = 0u;
+                bsi_mu_word<true, false, false>(found_q, n_found, t, aux_s, ctr, nullptr,
+                                                bsi_early_view(nullptr, 0), lanes);
+            }
         } else if (t < 2 * w32 && BSI_Q(t - w32, 0) < n_found) {
             bsi_key_word(found_q, n_found, t - w32);
         }
@@ -957,15 +1066,15 @@ bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words,
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
         if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
         bsi_finish_word<false>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
-                               ctr, steps, n_acc, n_rej, nullptr, &keep);
+                               ctr, steps, n_acc, n_rej, nullptr, &keep, 0u);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
 }
 
-#endif  // BSI_UNIT != 3
-#endif  // BSI_UNIT 3, 5
+#endif  // BSI_UNIT != 3, 6
+#endif  // BSI_UNIT 3, 5, 6
 
 #if BSI_UNIT == 0 || BSI_UNIT == 4
 // ---- attractor table: export / merge ------------------------------------------------------------

@@ -121,7 +121,9 @@ typedef struct bsi_plan_opts {
                                   [1] = full compares); costs atomics, for tuning only */
     uint32_t resolve_few_words;/* attract: queue length (words of 32 matched lanes) up to which the
                                   latency-oriented resolution kernels are used; 0 = auto (32768) */
-    uint32_t reserved[7];
+    uint32_t no_early_words;   /* attract: 1 = route every matched lane through per-lane records (turns
+                                  the bit-sliced early-word queue off; for comparison only) */
+    uint32_t reserved[6];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */
