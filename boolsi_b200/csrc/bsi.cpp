@@ -853,20 +853,24 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                 // the queue length (see bsi_template.cuh), the others return at once
                 uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
                 uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
-                void *args_k[] = {&p->found_q.p, &n_found_p, &few, &p->ctr.p};
                 void *args_m[] = {&p->found_q.p, &n_found_p, &few, &t_rel, &cap_l, &stop_cap, &p->table.p,
                                   &p->table_log2, &p->ctr.p};
                 unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
+                uint64_t early_cap = 0;
+                CUdeviceptr early_p = 0;
                 if (dense && !p->opts.no_early_words) {
-                    uint64_t word0 = b >> 5, early_cap = ((e + 31) >> 5) - word0;
+                    early_cap = ((e + 31) >> 5) - (b >> 5);
+                    early_p = p->early_q.p;
                     CUdeviceptr n_early_p = p->ctr.p + offsetof(Counters, n_early);
-                    void *args_e[] = {&p->early_q.p, &early_cap, &n_early_p, &t_rel, &cap_l, &stop_cap,
-                                      &p->table.p, &p->table_log2, &p->ctr.p};
+                    void *args_e[] = {&early_p, &early_cap, &n_early_p, &n_found_p, &few, &t_rel, &cap_l,
+                                      &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p};
                     if ((rc = launch(p, p->f_early, grid_m, p->block, 0, args_e))) return rc;
                 }
+                void *args_r[] = {&p->found_q.p, &n_found_p, &few, &early_p, &early_cap, &t_rel, &cap_l,
+                                  &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p};
                 if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
-                if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_k))) return rc;
+                if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_r))) return rc;
                 if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;
             }
             CU_CHECK(cuEventRecord(r1, p->stream));

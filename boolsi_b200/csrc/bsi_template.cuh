@@ -654,6 +654,11 @@ bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final
 // minimum state code (reference model.py:140-149 / attract.py:296).  Lane l of thread w walks
 // the cycle of found_q[32w + l] from y; walking more than lambda steps only revisits cycle
 // states, so all lanes of a word share the step count max lambda - 1.  lambda == 1: key = y.
+// latency mode = both queues are short (see the comment above bsi_resolve_mu)
+__device__ __forceinline__ bool bsi_latency_mode(u64 n_found, const BsiCounters *ctr, u64 few_words) {
+    return ((n_found + 31) >> 5) <= few_words && ctr->n_early <= few_words;
+}
+
 // in: cw_[32][KW] = on-cycle state codes of the valid lanes; out: their canonical keys, in place
 __device__ __forceinline__ void bsi_key_core(u64 (*cw_)[BSI_KW], u32 valid, u32 lam_max) {
     if (lam_max <= 1u) return;                    // fixed points: the state is its own key
@@ -969,9 +974,9 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
     }
 }
 
-// Two ways to run the resolution, chosen ON THE DEVICE from the queue length (the host launches
-// all three kernels; those that do not apply return at once):
-//  * many matched lanes (> few_words words): throughput matters -- bsi_resolve_mu reads every
+// Two ways to run the resolution, chosen ON THE DEVICE from the queue lengths (the host launches
+// all the kernels; those that do not apply return at once):
+//  * many matched lanes (> few_words words in either queue): throughput matters -- bsi_resolve_mu reads every
 //    record once, walks for the keys (when some cycle is longer than 1) and for mu, and finishes
 //    its lanes;
 //  * few matched lanes: the walks are latency-bound chains that form the tail after every
@@ -984,7 +989,7 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
-    if (((n_found + 31) >> 5) <= few_words) return;
+    if (bsi_latency_mode(n_found, ctr, few_words)) return;
     const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
     BsiKeep keep;
@@ -1008,11 +1013,13 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
 // The early-word queue of a dense round: keys, mu and aggregation of lanes that matched an early
 // checkpoint, straight from their bit-sliced states (no records, one transpose pass per word).
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, u64 T, u64 max_attractor_l,
-                  u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u64 *n_found_p,
+                  u64 few_words, u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
+                  u32 log2_slots, BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_early = *n_early_p;
     if (n_early == 0) return;
+    if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
     BsiKeep keep;
@@ -1032,24 +1039,41 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, u64 T, 
 #endif  // BSI_UNIT 6
 #if BSI_UNIT != 3 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, BsiCounters *ctr) {
+bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_base, u64 early_cap,
+            u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,
+            BsiCounters *ctr) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
-    if (((n_found + 31) >> 5) > few_words) return;
+    if (!bsi_latency_mode(n_found, ctr, few_words)) return;
     const u64 w32 = BSI_QWORDS(n_found);             // a multiple of 32
+    // third task range: the early-word queue (its kernel leaves it to this one when the record
+    // queue is short, so that all three kinds of walk run side by side)
+    const u64 n_early = early_cap ? ctr->n_early : 0ull;
+    const u64 e32 = (n_early + 31) & ~31ull;
+    const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
+    u64 steps = 0, n_acc = 0, n_rej = 0;
     for (;;) {
         const u64 t = bsi_grab_word(&ctr->next_word2);
-        if (__all_sync(0xFFFFFFFFu, t >= 2 * w32)) break;
+        if (__all_sync(0xFFFFFFFFu, t >= 2 * w32 + e32)) break;
         if (t < w32) {
             if (BSI_Q(t, 0) < n_found) {
                 u32 lanes = 0u;
                 bsi_mu_word<true, false, false>(found_q, n_found, t, aux_s, ctr, nullptr,
                                                 bsi_early_view(nullptr, 0), lanes);
             }
-        } else if (t < 2 * w32 && BSI_Q(t - w32, 0) < n_found) {
-            bsi_key_word(found_q, n_found, t - w32);
+        } else if (t < 2 * w32) {
+            if (BSI_Q(t - w32, 0) < n_found) bsi_key_word(found_q, n_found, t - w32);
+        } else if (t - 2 * w32 < n_early) {
+            BsiKeep keep;
+            u32 lanes = 0u;
+            bsi_mu_word<false, true, true>(nullptr, 0, t - 2 * w32, aux_s, ctr, &keep, eq, lanes);
+            bsi_finish_word<true>(nullptr, 0, t - 2 * w32, T, max_attractor_l, stop_t_cap, table,
+                                  log2_slots, ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
         }
     }
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
+    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
 }
 
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
@@ -1057,7 +1081,7 @@ bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words,
                    u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,
                    BsiCounters *ctr) {
     const u64 n_found = *n_found_p;
-    if (((n_found + 31) >> 5) > few_words) return;
+    if (!bsi_latency_mode(n_found, ctr, few_words)) return;
     const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
     BsiKeep keep;
