@@ -460,12 +460,7 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         o << " }\n#define BSI_CMP_REST(acc, X, Y) {";
         for (int i = 0; i < n; ++i)
             if (!in_filter[i]) o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", Y##" << i << ");";
-        o << " }\n#define BSI_CMP_REST_MEM(acc, X, P, S) {";
-        for (int i = 0; i < n; ++i)
-            if (!in_filter[i])
-                o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", (P)[(unsigned long long)" << i << " * (S)]);";
-        o << " }\n#define BSI_F2 " << std::max<size_t>(1, filter2.size()) << "\n";
-        o << "#define BSI_CMP_FILTER2_MEM(acc, X, P, S) {";
+        o << " }\n#define BSI_CMP_FILTER2_MEM(acc, X, P, S) {";
         for (size_t g = 0; g < filter2.size(); ++g)
             o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
@@ -565,19 +560,9 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         }
         o << "}\n";
     }
-    // code words <-> bit-sliced words, one lane at a time (rare paths)
-    {
-        o << "#define BSI_INSERT(X, l, c) {";
-        for (int i = 0; i < n; ++i)
-            o << " X##" << i << " |= (unsigned int)((c[" << (i >> 6) << "] >> " << (i & 63) << ") & 1ull) << (l);";
-        o << " }\n#define BSI_EXTRACT(X, l, c) {";
-        for (int w = 0; w < m.kw; ++w) o << " c[" << w << "] = 0ull;";
-        for (int i = 0; i < n; ++i)
-            o << " c[" << (i >> 6) << "] |= (unsigned long long)((X##" << i << " >> (l)) & 1u) << " << (i & 63) << ";";
-        o << " }\n";
-    }
-    // ... and all 32 lanes at once through 32x32 bit-matrix transposes (bsi_transpose32 maps
-    // B[r] bit c = A[31-c] bit 31-r, hence the reversed indices): CW is u64 [32 lanes][KW].
+    // code words <-> bit-sliced words: all 32 lanes at once through 32x32 bit-matrix transposes
+    // (bsi_transpose32 maps B[r] bit c = A[31-c] bit 31-r, hence the reversed indices): CW is
+    // u64 [32 lanes][KW].
     {
         const int blocks = (n + 31) / 32;
         o << "#define BSI_PACK(X, CW) { unsigned int A_[32];";

@@ -138,9 +138,7 @@ struct BsiRec {         // == bsi_attractor_rec (include/bsi.h)
 #define BSI_DECL_K1(i) BSI_DECL_ONE(k1_, i)
 #define BSI_DECL_K2(i) BSI_DECL_ONE(k2_, i)
 #define BSI_ZERO_A(i) a##i = 0u;
-#define BSI_ZERO_B(i) b##i = 0u;
 #define BSI_COPY_AB(i) a##i = b##i;
-#define BSI_COPY_BA(i) b##i = a##i;
 #define BSI_COPY_CA(i) c##i = a##i;
 #define BSI_SAVE_K0(i) k0_##i = a##i;
 #define BSI_SAVE_K1(i) k1_##i = a##i;
@@ -268,7 +266,7 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // themselves stay in shared memory / in a bit-sliced latch until the end of the word).
 extern __shared__ __align__(16) unsigned char bsi_smem[];
 
-// full compare of a state held in local memory with a checkpoint in the scratch: lanes of
+// full compare of a state held in local memory with a checkpoint in shared memory: lanes of
 // `cand` whose N words all agree
 __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u32 cstride, u32 cand) {
     // (a lane that passed both filters almost always matches, so there is no early exit)
@@ -280,7 +278,7 @@ __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u32 
 
 // detection record of the lanes in m: cycle length, checkpoint time and the matched state code
 // A match against a FINAL checkpoint (never overwritten) only notes the slot: the matched state
-// (= the checkpoint itself) and the previous checkpoint are extracted from the scratch at the end
+// (= the checkpoint itself) and the previous checkpoint are extracted from shared memory at the end
 // of the word, when all threads of the warp do so together instead of one diverged thread now.
 #define BSI_DEFERRED 0x80000000u
 // A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten)
@@ -1235,11 +1233,20 @@ bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lane
         }                                                                         \
     }
     BSI_STORE(a, 0)
-    for (u64 t = 1; t <= n_steps; ++t) {
+    // two steps per iteration (a -> b -> a): no register copies
+    u64 t = 1;
+    for (; t + 1 <= n_steps; t += 2) {
         BSI_UPDATE(b, a)
         if (perturbing) { BSI_PERTURB(b, t) }
-        BSI_FOR_NODES(BSI_COPY_AB)
-        BSI_STORE(a, t)
+        BSI_STORE(b, t)
+        BSI_UPDATE(a, b)
+        if (perturbing) { BSI_PERTURB(a, (t + 1)) }
+        BSI_STORE(a, (t + 1))
+    }
+    if (t <= n_steps) {
+        BSI_UPDATE(b, a)
+        if (perturbing) { BSI_PERTURB(b, t) }
+        BSI_STORE(b, t)
     }
 #undef BSI_STORE
 }
