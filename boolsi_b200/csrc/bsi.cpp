@@ -196,6 +196,7 @@ struct bsi_plan {
     int n_sms = 0;
     int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
     size_t main_smem = 0;
+    int smem_slots = 3;
     uint32_t table_log2 = 20;
     DevBuf ctr, table, found_q, retry_q[2], scratch, early_q, misc, misc2, misc3;
     std::vector<CUevent> events;
@@ -440,10 +441,18 @@ int compile_plan(bsi_plan *p) {
     tm.lap("choose_filter");
     p->block = p->opts.block_threads ? (int)p->opts.block_threads : 64;
     if (p->block % 32 != 0 || p->block > 1024) return fail(BSI_E_ARG, "block_threads must be a multiple of 32");
-    // register cap of the trajectory kernels: none by default (min_blocks = 6, i.e. 168 registers and
-    // 3 warps per scheduler, measured 1.7 % faster at N = 64 but spills filter words in the hot loop)
+    // Occupancy of the trajectory kernels.  A B200 scheduler owns 16 K registers: two warps fit at up
+    // to 255 registers per thread, a third needs <= 168 (min_blocks = 6) AND six 64-thread blocks of
+    // shared memory per SM (<= 37 KB each: smem_slots = 2 at N = 64, the third checkpoint slot in
+    // the L2-resident scratch).  Measured at N = 64, K = 3: 2.2 % faster when almost no lane closes
+    // (seed 0; the cap only spills slot-0 filter words in the three-slots-armed loop, 13 LDL per
+    // step) but 7 % slower when 13 % of the lanes close (seed 2: the match handlers spill).  Not the
+    // default; both knobs stay for tuning.
     const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
+    p->smem_slots = p->opts.smem_slots ? (int)p->opts.smem_slots : 3;
+    if (p->smem_slots < 1 || p->smem_slots > 3) return fail(BSI_E_ARG, "smem_slots must be 1, 2 or 3");
     p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info);
+    p->source += "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n";
     p->source += "\n#line 1 \"bsi_template.cuh\"\n";
     p->source += bsi_template_src;
     tm.lap("generate source");
@@ -520,7 +529,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
-        p->main_smem = (size_t)3 * p->m.n * p->block * 4;      // the three checkpoint slots
+        p->main_smem = (size_t)p->smem_slots * p->m.n * p->block * 4;      // the checkpoint slots held on chip
         if (p->main_smem > 48 * 1024) {
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
             CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
@@ -792,7 +801,8 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
     const size_t found_bytes = 24 + 24 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    const size_t scratch_bytes = (size_t)main_grid * p->block * 96 * sizeof(uint32_t);
+    // per thread: detection records (3 x 32 words) + the checkpoint slots that are not in shared memory
+    const size_t scratch_bytes = (size_t)main_grid * p->block * (96 + (size_t)(3 - p->smem_slots) * p->m.n) * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));

@@ -242,6 +242,41 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
     return base + (incl - n);
 }
 
+// Warp-aggregated table update, called by ALL 32 threads of a warp (n == 0: nothing to add).
+// In the ordered regime millions of lanes fall into a handful of attractors: one atomicAdd
+// triple per THREAD then serialises on a few L2 addresses (measured: 2.3 ns per word, the whole
+// resolution time).  Threads holding the same key are summed with shuffles and their first
+// lane adds once; after a few rounds (many distinct keys in the warp: nothing to gain) the
+// remaining threads add for themselves.
+__device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slots, const u64 *key, u64 n,
+                                                   u64 s1, u64 s2, u32 lam, BsiCounters *ctr) {
+    const u32 lane = threadIdx.x & 31u;
+    u32 pending = __ballot_sync(0xFFFFFFFFu, n != 0ull);
+#pragma unroll 1
+    for (int round = 0; pending && round < 4; ++round) {
+        const u32 leader = __ffs(pending) - 1;
+        bool same = n != 0ull;
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) {
+            const u64 k = __shfl_sync(0xFFFFFFFFu, key[i], leader);     // (every thread takes part:
+            same = same && (k == key[i]);                               //  no short-circuit around it)
+        }
+        const u32 grp = __ballot_sync(0xFFFFFFFFu, same);
+        u64 a = same ? n : 0ull, b = same ? s1 : 0ull, c = same ? s2 : 0ull;
+        if (grp != (1u << leader)) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, d);
+                c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+            }
+        }
+        if (lane == leader) bsi_table_add(table, log2_slots, key, a, b, c, lam, ctr);
+        pending &= ~grp;
+    }
+    if ((pending >> lane) & 1u) bsi_table_add(table, log2_slots, key, n, s1, s2, lam, ctr);
+}
+
 // perturbation prefix: LP steps from t = 0, perturbations overriding at their time
 // (reference model.py:76-128).  Ends with the state at time LP in a*.
 #define BSI_PREFIX(LP)                                                              \
@@ -268,7 +303,7 @@ extern __shared__ __align__(16) unsigned char bsi_smem[];
 
 // full compare of a state held in local memory with a checkpoint in shared memory: lanes of
 // `cand` whose N words all agree
-__device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u32 cstride, u32 cand) {
+__device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 cstride, u32 cand) {
     // (a lane that passed both filters almost always matches, so there is no early exit)
     u32 acc = ~cand;
 #pragma unroll 8
@@ -316,6 +351,14 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     // detection records of this thread's 32 lanes (rarely written), in global memory
     u32 *const lam_s = scratch + gtid;                                // [32][sstride]
     u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride], then c0 [32]
+    // checkpoint slot S: the first BSI_SMEM_SLOTS slots live in shared memory, the later ones
+    // (armed for the shortest time) in this thread's scratch, [slot][node][sstride], L2-resident
+    u32 *const ck_g = scratch + 96ull * sstride + gtid;
+    (void)ck_g;
+#define BSI_CK_ONCHIP(S) (BSI_SMEM_SLOTS == 3 || (S) < BSI_SMEM_SLOTS)
+#define BSI_CK_PTR(S) (BSI_CK_ONCHIP(S) ? ck_s + (S) * BSI_N * BSI_BLOCK \
+                                            : ck_g + (u64)((S) - BSI_SMEM_SLOTS) * BSI_N * sstride)
+#define BSI_CK_STRIDE(S) (BSI_CK_ONCHIP(S) ? (u64)BSI_BLOCK : sstride)
     u64 dev_steps = 0, n_without = 0, ref_steps = 0;
 
     for (;;) {
@@ -373,7 +416,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         u32 cand_ = ~(ACC) & alive;                                                  \
         if (cand_) {                                                                 \
             BSI_COUNT(1)                                                             \
-            u32 m_ = bsi_slow_match(XS, ck_s + (S) * BSI_N * BSI_BLOCK, BSI_BLOCK, cand_); \
+            u32 m_ = bsi_slow_match(XS, BSI_CK_PTR(S), BSI_CK_STRIDE(S), cand_);       \
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
@@ -391,8 +434,8 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #define BSI_STAGE2(X, S, ACC)                                                        \
     if (ACC != 0xFFFFFFFFu) {                                                        \
         BSI_COUNT(0)                                                                 \
-        const u32 *p2_ = ck_s + (S) * BSI_N * BSI_BLOCK;                              \
-        BSI_CMP_FILTER2_MEM(ACC, X, p2_, BSI_BLOCK)                                  \
+        const u32 *p2_ = BSI_CK_PTR(S);                                              \
+        BSI_CMP_FILTER2_MEM(ACC, X, p2_, BSI_CK_STRIDE(S))                           \
     }
             // register filters of state X against the armed slots: p_s = lanes that CANNOT match
 #define BSI_FILT0(X) {}
@@ -502,8 +545,13 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 // checkpoint due at time j: state a (already compared) goes into its slot
                 if (ci < sched.n_ck && sched.ck_time[ci] == j) {
                     const u32 s = sched.ck_slot[ci];
-                    u32 *p_ = ck_s + s * BSI_N * BSI_BLOCK;
-                    BSI_STORE_ALL(a, p_, BSI_BLOCK)
+                    if (BSI_CK_ONCHIP(s)) {
+                        u32 *p_ = ck_s + s * BSI_N * BSI_BLOCK;
+                        BSI_STORE_ALL(a, p_, BSI_BLOCK)
+                    } else {
+                        u32 *p_ = ck_g + (u64)(s - BSI_SMEM_SLOTS) * BSI_N * sstride;
+                        BSI_STORE_ALL(a, p_, sstride)
+                    }
                     if (s == 0u) { BSI_FOR_FILTER(BSI_SAVE_K0) st0 = j; }
                     else if (s == 1u) { BSI_FOR_FILTER(BSI_SAVE_K1) st1 = j; }
                     else { BSI_FOR_FILTER(BSI_SAVE_K2) st2 = j; }
@@ -572,19 +620,21 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 if (r.c0 & BSI_DEFERRED) {
                     // y = the matched final checkpoint, z = the final checkpoint before it
                     const u32 slot = r.c0 & 3u;
-                    const u32 *py = ck_s + slot * BSI_N * BSI_BLOCK;
-                    const u32 *pz = py - BSI_N * BSI_BLOCK;
+                    const u32 *py = BSI_CK_PTR(slot);
+                    const u64 sy = BSI_CK_STRIDE(slot);
+                    const u32 *pz = BSI_CK_PTR(slot ? slot - 1u : 0u);
+                    const u64 sz = BSI_CK_STRIDE(slot ? slot - 1u : 0u);
                     r.c0 = slot == 0u ? 0u : (slot == 1u ? st0 : st1);
 #pragma unroll
                     for (int k = 0; k < BSI_KW; ++k) {
                         u64 y = 0ull, z = 0ull;
 #pragma unroll 8
                         for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
-                            y |= (u64)((py[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
+                            y |= (u64)((py[i * sy] >> l) & 1u) << (i & 63);
                         if (slot) {
 #pragma unroll 8
                             for (int i = 64 * k; i < BSI_N && i < 64 * k + 64; ++i)
-                                z |= (u64)((pz[i * BSI_BLOCK] >> l) & 1u) << (i & 63);
+                                z |= (u64)((pz[i * sz] >> l) & 1u) << (i & 63);
                         }
                         r.y[k] = y; r.key[k] = y; r.z[k] = z;
                     }
@@ -906,7 +956,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 // Acceptance (mu + lambda <= T, lambda <= max_attractor_l; reference attract.py:287-300) and
 // aggregation into the attractor table (attract.py:374-402) of the 32 lanes of word w; lanes of
 // one thread with equal keys are added once.
-template <bool FROM_KEEP>
+template <bool FROM_KEEP, bool WARP_AGG>
 __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_found, u64 w, u64 T,
                                                 u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
                                                 u32 log2_slots, BsiCounters *ctr, u64 &steps,
@@ -933,12 +983,15 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
             }
         }
         // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
-        while (todo) {
-            const u32 l0 = __ffs(todo) - 1;
+        // (WARP_AGG: every thread of the warp is here, idle ones with todo == 0, and the loop is
+        // warp-uniform so that threads holding the same key can be summed before the atomics)
+        for (;;) {
+            if (WARP_AGG ? !__any_sync(0xFFFFFFFFu, todo != 0u) : !todo) break;
+            const u32 l0 = todo ? __ffs(todo) - 1 : 0u;
             u64 key0[BSI_KW];
 #pragma unroll
-            for (int i = 0; i < BSI_KW; ++i) key0[i] = keep->key[l0][i];
-            const u32 lam0 = keep->lam[l0];
+            for (int i = 0; i < BSI_KW; ++i) key0[i] = todo ? keep->key[l0][i] : 0ull;
+            const u32 lam0 = todo ? keep->lam[l0] : 0u;
             u64 n = 0, s1 = 0, s2 = 0;
             u32 rest = todo;
             while (rest) {
@@ -964,9 +1017,12 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                     ++n_rej;
                 }
             }
-            if (n) {
+            n_acc += n;
+            if (WARP_AGG) {
+                __syncwarp();
+                bsi_warp_table_add(table, log2_slots, key0, n, s1, s2, lam0, ctr);
+            } else if (n) {
                 bsi_table_add(table, log2_slots, key0, n, s1, s2, lam0, ctr);
-                n_acc += n;
             }
         }
     }
@@ -995,11 +1051,12 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
-        if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
-        u32 lanes = 0u;
-        bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, lanes);
-        bsi_finish_word<true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
-                              ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
+        u32 lanes = 0u;                  // threads without a word stay for the warp-level aggregation
+        if (w < n_words && BSI_Q(w, 0) < n_found)
+            bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, lanes);
+        __syncwarp();
+        bsi_finish_word<true, true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
+                                    ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
@@ -1024,11 +1081,11 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u
     for (;;) {
         const u64 e = bsi_grab_word(&ctr->next_word4);
         if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
-        if (e >= n_early) continue;
         u32 lanes = 0u;
-        bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, lanes);
-        bsi_finish_word<true>(nullptr, 0, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
-                              steps, n_acc, n_rej, aux_s, &keep, lanes);
+        if (e < n_early) bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, lanes);
+        __syncwarp();
+        bsi_finish_word<true, true>(nullptr, 0, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
+                                    steps, n_acc, n_rej, aux_s, &keep, lanes);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
@@ -1065,7 +1122,7 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
             BsiKeep keep;
             u32 lanes = 0u;
             bsi_mu_word<false, true, true>(nullptr, 0, t - 2 * w32, aux_s, ctr, &keep, eq, lanes);
-            bsi_finish_word<true>(nullptr, 0, t - 2 * w32, T, max_attractor_l, stop_t_cap, table,
+            bsi_finish_word<true, false>(nullptr, 0, t - 2 * w32, T, max_attractor_l, stop_t_cap, table,
                                   log2_slots, ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
         }
     }
@@ -1087,7 +1144,7 @@ bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words,
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
         if (w >= n_words || BSI_Q(w, 0) >= n_found) continue;
-        bsi_finish_word<false>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
+        bsi_finish_word<false, false>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
                                ctr, steps, n_acc, n_rej, nullptr, &keep, 0u);
     }
     if (steps) atomicAdd(&ctr->steps, steps);

@@ -123,7 +123,10 @@ typedef struct bsi_plan_opts {
                                   latency-oriented resolution kernels are used; 0 = auto (32768) */
     uint32_t no_early_words;   /* attract: 1 = route every matched lane through per-lane records (turns
                                   the bit-sliced early-word queue off; for comparison only) */
-    uint32_t reserved[6];
+    uint32_t smem_slots;       /* attract: how many of the three checkpoint slots live in shared memory
+                                  (the others in the thread's L2-resident scratch); 0 = auto (3).
+                                  2 with min_blocks 6 buys a third warp per scheduler at N = 64 */
+    uint32_t reserved[5];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */

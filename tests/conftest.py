@@ -23,6 +23,12 @@ def _have_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _have_gpu():
+        # a kernel that never returns must not eat the GPU box's time limit: the thread method
+        # ends the process even while the main thread sits in a driver call
+        if config.pluginmanager.hasplugin('timeout'):
+            for item in items:
+                if 'gpu' in item.keywords and item.get_closest_marker('timeout') is None:
+                    item.add_marker(pytest.mark.timeout(240, method='thread'))
         return
     skip = pytest.mark.skip(reason='no CUDA device in this container')
     for item in items:

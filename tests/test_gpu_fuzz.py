@@ -55,7 +55,10 @@ def test_attract_fuzz(seed):
     max_a = [inf, inf, int(rng.integers(1, 6))][(seed // 3) % 3]
     lo = int(rng.integers(0, sp.n_problems))
     hi = int(rng.integers(lo, sp.n_problems + 1))
-    with _lib.Plan(pk, _lib.MODE_ATTRACT, first_horizon=[0, 1, 7, 64][seed % 4]) as plan:
+    # resolve_few_words = 1 sends even these small cases through the throughput-mode resolution
+    # kernels (warp-aggregated table updates); no_early_words = 1 through per-lane records only
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, first_horizon=[0, 1, 7, 64][seed % 4],
+                   resolve_few_words=[0, 1][(seed // 2) % 2], no_early_words=[0, 0, 1][seed % 3]) as plan:
         for b, e in ((0, sp.n_problems), (lo, hi)):
             plan.table_clear()
             st = plan.attract_run(b, e, max_t, max_a)
@@ -66,6 +69,35 @@ def test_attract_fuzz(seed):
             assert got == want
             assert st['steps'] == rec['steps']
             assert st['n_without'] == int((rec['found'] == 0).sum())
+
+
+@pytest.mark.parametrize('opts', [dict(resolve_few_words=1), dict(resolve_few_words=1, no_early_words=1), {}],
+                         ids=['throughput', 'throughput-records', 'auto'])
+@pytest.mark.parametrize('n_free', [5, 12, 15])
+def test_attract_many_attractors_per_warp(n_free, opts):
+    """Every node keeps its state except a few that fall into short cycles: up to 2^n_free
+    different attractors, so that the threads of a warp hold many different keys at once (the
+    warp-level aggregation must fall back to per-thread table updates) -- against the C oracle."""
+    n = 20
+    preds = [[i] for i in range(n)]
+    tts = [{(False,): False, (True,): True} for _ in range(n)]
+    preds[17], tts[17] = [18], {(False,): False, (True,): True}          # 17 <- 18 <- 19 <- not 17
+    preds[18], tts[18] = [19], {(False,): False, (True,): True}
+    preds[19], tts[19] = [17], {(False,): True, (True,): False}
+    preds[16], tts[16] = [3, 16], {(False, False): False, (False, True): True, (True, False): True, (True, True): False}
+    origin = ([False] * n, {}, {})
+    variations = (list(range(n_free)) + [17, 19], [], [])
+    sp = coracle.Space(preds, tts, origin, variations)
+    pk = _lib.PackedProblem(preds, tts, origin, variations)
+    rec = coracle.attract_records(sp, 50, inf)
+    want = sorted((k, v[0], v[1], v[2], v[3]) for k, v in coracle.attract_table(rec, sp.kw).items())
+    assert len(want) >= 1 << (n_free - 1)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, table_log2_slots=18, **opts) as plan:
+        st = plan.attract_run(0, pk.n_problems, 50, inf)
+        got = sorted((_lib.code_from_words(r['key'][:pk.kw]), int(r['n']), int(r['sum_l']), int(r['sum_l2']),
+                      int(r['lam'])) for r in plan.table_read(1 << 17))
+        assert got == want
+        assert st['steps'] == rec['steps']
 
 
 @pytest.mark.parametrize('seed', range(16))

@@ -57,6 +57,26 @@ def test_attract_horizon_rounds(name, first_horizon):
         assert st['steps'] == case['expected']['steps']
 
 
+@pytest.mark.parametrize('opts', [dict(smem_slots=3, min_blocks=1), dict(smem_slots=2, min_blocks=6),
+                                  dict(smem_slots=1, min_blocks=1), dict(smem_slots=2, block_threads=32)],
+                         ids=lambda o: '-'.join('%s%d' % (k[:4], v) for k, v in o.items()))
+@pytest.mark.parametrize('name', ['attract_rnd64k2s0_f10_t5000_ainf', 'attract_rnd20k2s3_f12_tinf_ainf',
+                                  'attract_rulesA_fixed_perturbed', 'attract_rnd33k3s2_f10_t400_ainf'])
+def test_attract_checkpoint_placement(name, opts):
+    """Where the checkpoint slots live (shared memory or the L2-resident scratch) and the register
+    cap are tuning choices: every combination gives the reference's result."""
+    case = [c for c in goldenlib.cases('attract') if c['name'] == name][0]
+    a = goldenlib.case_args(case)
+    pk = _packed(a)
+    with _lib.Plan(pk, _lib.MODE_ATTRACT, **opts) as plan:
+        st = plan.attract_run(0, pk.n_problems, a['max_t'], a['max_attractor_l'])
+        want = goldenlib.expected_attractor_rows(case)
+        assert _table_rows(plan) == [(k, n, s1, s2, len(cyc)) for k, n, s1, s2, cyc in want]
+        assert st['steps'] == case['expected']['steps']
+        for k, n, s1, s2, cyc in want[:4]:
+            assert plan.attractor_states(k, len(cyc)) == cyc
+
+
 def test_attract_ranges_accumulate_and_clear():
     case = [c for c in goldenlib.cases('attract') if c['name'] == 'attract_cambium2_first12'][0]
     a = goldenlib.case_args(case)
@@ -134,11 +154,12 @@ def test_attract_vs_c_oracle(n_nodes, k, seed, n_free, max_t, max_a, lo, hi):
     pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
                             cfg['origin simulation problem'], cfg['simulation problem variations'])
     want_rows, want_steps, want_without = _oracle_table(cfg, max_t, max_a, lo, hi)
-    with _lib.Plan(pk, _lib.MODE_ATTRACT) as plan:
-        st = plan.attract_run(lo, hi, max_t, max_a)
-        assert _table_rows(plan) == want_rows
-        assert st['steps'] == want_steps
-        assert st['n_without'] == want_without
+    for opts in ({}, dict(smem_slots=3, min_blocks=1), dict(smem_slots=2, min_blocks=6)):
+        with _lib.Plan(pk, _lib.MODE_ATTRACT, **opts) as plan:
+            st = plan.attract_run(lo, hi, max_t, max_a)
+            assert _table_rows(plan) == want_rows
+            assert st['steps'] == want_steps
+            assert st['n_without'] == want_without
 
 
 def test_attract_random_free_subset_vs_c_oracle():

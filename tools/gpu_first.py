@@ -23,7 +23,11 @@ for opts in variants:
         tsps = st['steps'] / (st['ms_total'] * 1e-3)
         print(rep, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()},
               'steps/s %.3e' % tsps, 'lop3 alg frac %.3f' % (tsps * 4.0 / out['peak']['lop3_per_s']), flush=True)
-    print('attractors', plan.table_count(), flush=True)
+    import hashlib
+    rows = sorted((_lib.code_from_words(r['key'][:pk.kw]), int(r['n']), int(r['sum_l']), int(r['sum_l2']),
+                   int(r['lam'])) for r in plan.table_read())
+    print('attractors', plan.table_count(), 'table sha', hashlib.sha1(repr(rows).encode()).hexdigest()[:12],
+          'steps', st['steps'], flush=True)
     out[str(opts)] = st
     plan.close()
 json.dump(out, open('gpurun_out/gpu_first.json', 'w'), indent=1, default=str)
