@@ -4,6 +4,8 @@ The library is the product: there is no Python or CPU implementation of the path
 missing library or missing CUDA device is an error, never a fallback.
 """
 import ctypes as C
+import functools
+import itertools
 import os
 from math import inf
 
@@ -194,11 +196,10 @@ class PackedProblem:
         pred_idx, tt = [], []
         for i, (preds, table) in enumerate(zip(predecessor_node_lists, truth_tables)):
             k = len(preds)
-            pred_idx.extend(int(q) for q in preds)
-            for j in range(1 << k):
-                # first predecessor = most significant bit of j (input.py:881, model.py:26-27)
-                key = tuple(bool((j >> (k - 1 - m)) & 1) for m in range(k))
-                tt.append(1 if table[key] else 0)
+            pred_idx.extend(preds)
+            # entry j: first predecessor = most significant bit of j, which is the order of
+            # itertools.product((False, True), repeat=k) (input.py:881, model.py:26-27)
+            tt.extend(map(table.__getitem__, _tt_keys(k)))
             pred_off[i + 1] = len(pred_idx)
             tt_off[i + 1] = len(tt)
         initial_state, fixed_nodes, perturbed_nodes_by_t = origin_simulation_problem
@@ -240,6 +241,11 @@ class PackedProblem:
         for name in ('initial_state', 'fixed_node', 'fixed_value', 'pert_t', 'pert_node',
                      'pert_value', 'var_kind', 'var_node', 'var_t', 'var_range'):
             setattr(sp, name, _ptr(a[name]))
+
+
+@functools.lru_cache(maxsize=None)
+def _tt_keys(k):
+    return tuple(itertools.product((False, True), repeat=k))
 
 
 def make_target(target_node_set, target_substate_code, kw):
@@ -306,6 +312,11 @@ class Plan:
         data, size = C.c_void_p(), C.c_uint64()
         check(lib().bsi_plan_cubin(self._h, C.byref(data), C.byref(size)))
         return C.string_at(data, size.value)
+
+    def cubin_bytes(self):
+        data, size = C.c_void_p(), C.c_uint64()
+        check(lib().bsi_plan_cubin(self._h, C.byref(data), C.byref(size)))
+        return int(size.value)
 
     def op_counts(self):
         u, c, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
@@ -386,12 +397,17 @@ class Plan:
 
     def attractor_states_batch(self, keys_and_lams, as_words=False):
         """[(key, lam), ...] -> [[state codes, key first], ...] (or, with `as_words`, uint64 arrays
-        [lam, key_words]); one launch per power-of-two length class so that a long cycle does not
-        inflate the buffers of the short ones."""
+        [lam, key_words]).  One launch when the padded result (every orbit as long as the longest)
+        stays small; otherwise one launch per power-of-two length class, so that a long cycle does
+        not inflate the buffers of many short ones."""
         out = [None] * len(keys_and_lams)
+        if not keys_and_lams:
+            return out
         groups = {}
+        longest = max(int(lam) for _, lam in keys_and_lams)
+        one_launch = len(keys_and_lams) * longest * self.kw * 8 <= (32 << 20)
         for pos, (key, lam) in enumerate(keys_and_lams):
-            groups.setdefault(max(1, int(lam) - 1).bit_length(), []).append(pos)
+            groups.setdefault(0 if one_launch else max(1, int(lam) - 1).bit_length(), []).append(pos)
         for _, members in sorted(groups.items()):
             n_states = max(int(keys_and_lams[pos][1]) for pos in members)
             keys = np.zeros((len(members), self.kw), np.uint64)

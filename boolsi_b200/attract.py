@@ -114,7 +114,7 @@ def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_prob
     try:
         eng.run(max_t, max_attractor_l)
         attractors = eng.attractors()
-        h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + len(eng.plan.cubin()) + \
+        h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + eng.plan.cubin_bytes() + \
             8 * eng.plan.kw * len(attractors)
         d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * len(a.states) for a in attractors) + 128
         return {'attractors': attractors, 'n_attractors': len(attractors),

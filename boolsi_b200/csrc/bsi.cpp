@@ -181,7 +181,7 @@ struct bsi_plan {
     bsi::GenInfo info;
     bsi_plan_opts opts{};
     std::string source, log;
-    std::vector<char> cubins[7];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 + 6 resolve, 4 the rest)
+    std::shared_ptr<const std::vector<char>> cubins[7];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 + 6 resolve, 4 the rest)
     int block = 64;
     int device = -1;           // -1: compile-only plan
     CUdevice dev = 0;
@@ -360,22 +360,9 @@ struct UnitResult {
     std::vector<char> cubin;
 };
 
-// One NVRTC program -> sm_100a cubin, with an in-process cache keyed by the source text (the
-// same network + space + mode specialises to the same source).
+// One NVRTC program -> sm_100a cubin.
 UnitResult compile_unit(std::string src) {
-    static std::mutex cache_mu;
-    static std::map<std::string, std::pair<std::vector<char>, std::string>> cache;
     UnitResult out;
-    out.key = std::to_string(src.size()) + ":" + std::to_string(std::hash<std::string>()(src));
-    {
-        std::lock_guard<std::mutex> lk(cache_mu);
-        auto it = cache.find(src);
-        if (it != cache.end()) {
-            out.cubin = it->second.first;
-            out.log = it->second.second;
-            return out;
-        }
-    }
     nvrtcProgram prog;
     nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "bsi_kernels.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) {
@@ -409,13 +396,17 @@ UnitResult compile_unit(std::string src) {
     out.cubin.resize(cubin_size);
     nvrtcGetCUBIN(prog, out.cubin.data());
     nvrtcDestroyProgram(&prog);
-    {
-        std::lock_guard<std::mutex> lk(cache_mu);
-        if (cache.size() >= 256) cache.clear();
-        cache[src] = {out.cubin, out.log};
-    }
     return out;
 }
+
+// In-process cache of compiled units.  The template text is a constant of the library, so a unit is
+// identified by the generated header (network + space + mode + tuning) and its BSI_UNIT number.
+struct CachedUnit {
+    std::shared_ptr<const std::vector<char>> cubin;
+    std::string log, key;
+};
+std::mutex g_unit_mu;
+std::map<std::pair<std::string, int>, CachedUnit> g_units;
 
 int compile_plan(bsi_plan *p) {
     StageTimer tm;
@@ -451,29 +442,49 @@ int compile_plan(bsi_plan *p) {
     const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
     p->smem_slots = p->opts.smem_slots ? (int)p->opts.smem_slots : 3;
     if (p->smem_slots < 1 || p->smem_slots > 3) return fail(BSI_E_ARG, "smem_slots must be 1, 2 or 3");
-    p->source = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info);
-    p->source += "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n";
-    p->source += "\n#line 1 \"bsi_template.cuh\"\n";
-    p->source += bsi_template_src;
+    const std::string header = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info) +
+                               "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n";
+    p->source = header + "\n#line 1 \"bsi_template.cuh\"\n" + bsi_template_src;
     tm.lap("generate source");
 
     // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
-    // thread-safe across programs): the two trajectory kernels dominate the compile time.
+    // thread-safe across programs): the two trajectory kernels dominate the compile time.  Units
+    // already compiled in this process come from the cache without starting a thread.
     std::vector<int> units;
     if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 5, 6, 4}; else units = {4};
-    std::vector<std::future<UnitResult>> jobs;
-    for (int u : units) {
-        std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
-        jobs.push_back(std::async(std::launch::async, compile_unit, std::move(src)));
+    std::vector<std::pair<int, std::future<UnitResult>>> jobs;
+    p->log.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_unit_mu);
+        for (int u : units) {
+            auto it = g_units.find({header, u});
+            if (it != g_units.end()) {
+                p->cubins[u] = it->second.cubin;
+                p->unit_key[u] = it->second.key;
+                if (!it->second.log.empty()) p->log += it->second.log + "\n";
+            } else {
+                std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
+                jobs.emplace_back(u, std::async(std::launch::async, compile_unit, std::move(src)));
+            }
+        }
     }
     int rc = BSI_OK;
-    p->log.clear();
-    for (size_t i = 0; i < units.size(); ++i) {
-        UnitResult r = jobs[i].get();
-        if (r.status != BSI_OK && rc == BSI_OK) { rc = r.status; g_err = r.error; }
-        if (!r.log.empty()) p->log += r.log + "\n";
-        p->cubins[units[i]] = std::move(r.cubin);
-        p->unit_key[units[i]] = r.key;
+    for (auto &job : jobs) {
+        UnitResult r = job.second.get();
+        if (r.status != BSI_OK) {
+            if (rc == BSI_OK) { rc = r.status; g_err = r.error; }
+            continue;
+        }
+        CachedUnit c;
+        c.cubin = std::make_shared<const std::vector<char>>(std::move(r.cubin));
+        c.log = r.log;
+        c.key = std::to_string(header.size()) + ":" + std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(job.first);
+        if (!c.log.empty()) p->log += c.log + "\n";
+        p->cubins[job.first] = c.cubin;
+        p->unit_key[job.first] = c.key;
+        std::lock_guard<std::mutex> lk(g_unit_mu);
+        if (g_units.size() >= 1024) g_units.clear();
+        g_units[{header, job.first}] = std::move(c);
     }
     tm.lap("nvrtc (parallel units)");
     p->source = "#define BSI_UNIT 0\n" + p->source;       // what bsi_plan_source shows: the whole TU
@@ -501,7 +512,7 @@ int load_plan(bsi_plan *p, int device) {
         static std::map<std::string, CUmodule> loaded;
         std::lock_guard<std::mutex> lk(g_dev_mu);
         for (int u = 1; u <= 6; ++u) {
-            if (p->cubins[u].empty()) continue;
+            if (!p->cubins[u] || p->cubins[u]->empty()) continue;
             const std::string key = std::to_string(device) + "/" + p->unit_key[u];
             auto it = loaded.find(key);
             if (it != loaded.end()) {
@@ -509,7 +520,7 @@ int load_plan(bsi_plan *p, int device) {
                 p->mod_cached[u] = true;
                 continue;
             }
-            CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u].data()));
+            CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u]->data()));
             if (loaded.size() < 128) {
                 loaded[key] = p->mods[u];
                 p->mod_cached[u] = true;
@@ -716,7 +727,9 @@ const char *bsi_plan_build_log(const bsi_plan *p) { return p ? p->log.c_str() : 
 
 int bsi_plan_cubin(const bsi_plan *p, const void **data, uint64_t *bytes) {
     if (!p || !data || !bytes) return fail(BSI_E_ARG, "null pointer");
-    const std::vector<char> &c = p->cubins[p->m.mode == BSI_MODE_ATTRACT ? 1 : 4];
+    static const std::vector<char> none;
+    const auto &cp = p->cubins[p->m.mode == BSI_MODE_ATTRACT ? 1 : 4];
+    const std::vector<char> &c = cp ? *cp : none;
     *data = c.data();
     *bytes = c.size();
     return BSI_OK;
@@ -750,7 +763,7 @@ int bsi_compile_only(const bsi_network_desc *network, const bsi_space_desc *spac
         snprintf(log, (size_t)log_cap, "%s", src.c_str());
     }
     if (rc == BSI_OK) {
-        if (cubin_bytes) { *cubin_bytes = 0; for (auto &c : p->cubins) *cubin_bytes += c.size(); }
+        if (cubin_bytes) { *cubin_bytes = 0; for (auto &c : p->cubins) if (c) *cubin_bytes += c->size(); }
         bsi_plan_destroy(p);
     }
     return rc;
@@ -838,7 +851,7 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                 // early-word queue: one entry per word at most
                 uint64_t early_cap = p->opts.no_early_words ? 0 : n_words;
                 if (early_cap &&
-                    (rc = ensure(p, p->early_q, early_cap * (8 + 4 + 32 * 8 + 4 * (size_t)p->m.n) + 256)))
+                    (rc = ensure(p, p->early_q, ((early_cap + 31) / 32) * 32 * (8 + 4 + 32 * 8 + 4 * (size_t)p->m.n))))   // whole blocks of 32 entries
                     return rc;
                 CUdeviceptr early_p = early_cap ? p->early_q.p : 0;
                 void *args[] = {&word0, &n_words, &b, &e, &sched, (void *)&final_round, &stop_t,

@@ -99,23 +99,39 @@ struct BsiFound {       // one lane that matched a checkpoint
 };
 
 // Early-word queue (dense rounds only): a word whose lanes matched EARLY checkpoints hands them
-// over bit-sliced -- no per-lane records, no transposes.  Structure of arrays over the entry e:
-//   u64 word[cap]; u32 mask[cap]; u64 lamc[32][cap] (lambda | c << 32); u32 y[N][cap] (the latch)
+// over bit-sliced -- no per-lane records, no transposes.  Entries come in blocks of 32 (the 32
+// threads of a warp reserve consecutive entries and later read consecutive entries), and a block
+// is one contiguous piece of memory, structure of arrays inside:
+//   u64 word[32]; u64 lamc[32 lanes][32] (lambda | c << 32); u32 mask[32]; u32 y[N][32] (the latch)
+// so that a warp's ~100 loads per entry hit a few adjacent DRAM pages instead of 100 planes that
+// lie `cap` entries apart (measured: the plane layout kept the resolution kernel waiting on
+// memory for a third of its time).
+#define BSI_EQ_BLOCK_BYTES (32ull * (8ull + 32ull * 8ull + 4ull + 4ull * BSI_N))
 struct BsiEarlyQ {
-    u64 *word;
-    u32 *mask;
-    u64 *lamc;
-    u32 *y;
+    unsigned char *base;
     u64 cap;
+};
+struct BsiEarlyEntry {
+    u64 *word;          // [0]
+    u64 *lamc;          // [lane * 32]
+    u32 *mask;          // [0]
+    u32 *y;             // [node * 32]
 };
 __device__ __forceinline__ BsiEarlyQ bsi_early_view(void *base, u64 cap) {
     BsiEarlyQ q;
+    q.base = (unsigned char *)base;
     q.cap = cap;
-    q.word = (u64 *)base;
-    q.lamc = q.word + cap;
-    q.mask = (u32 *)(q.lamc + 32ull * cap);
-    q.y = q.mask + cap;
     return q;
+}
+__device__ __forceinline__ BsiEarlyEntry bsi_early_entry(const BsiEarlyQ &q, u64 e) {
+    unsigned char *blk = q.base + (e >> 5) * BSI_EQ_BLOCK_BYTES;
+    const u32 k = (u32)e & 31u;
+    BsiEarlyEntry r;
+    r.word = (u64 *)blk + k;
+    r.lamc = (u64 *)blk + 32 + k;
+    r.mask = (u32 *)(blk + 33ull * 32ull * 8ull) + k;
+    r.y = r.mask + 32;
+    return r;
 }
 
 struct BsiSlot {
@@ -578,17 +594,17 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         if (DENSE && early_cap) {
             const u64 e = bsi_reserve(&ctr->n_early, early ? 1u : 0u);
             if (early) {
-                const BsiEarlyQ q = bsi_early_view(early_base, early_cap);
-                q.word[e] = word0 + w;
-                q.mask[e] = early;
-                u32 m = early;
-                while (m) {
-                    const u32 l = __ffs(m) - 1;
-                    m &= m - 1;
-                    q.lamc[l * early_cap + e] = (u64)lam_s[l * sstride] | ((u64)c_s[l * sstride] << 32);
-                }
+                const BsiEarlyEntry q = bsi_early_entry(bsi_early_view(early_base, early_cap), e);
+                q.word[0] = word0 + w;
+                q.mask[0] = early;
+                // (unrolled with predication, not a loop over the set bits: the record loads are
+                // L2 round trips, and a word of the ordered regime has all 32 lanes here)
 #pragma unroll 8
-                for (int i = 0; i < BSI_N; ++i) q.y[i * early_cap + e] = yl_[i];
+                for (u32 l = 0; l < 32; ++l)
+                    if ((early >> l) & 1u)
+                        q.lamc[l * 32u] = (u64)lam_s[l * sstride] | ((u64)c_s[l * sstride] << 32);
+#pragma unroll 8
+                for (int i = 0; i < BSI_N; ++i) q.y[i * 32] = yl_[i];
                 F &= ~early;
                 early = 0u;
             }
@@ -781,8 +797,8 @@ struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it
     u32 lam[32], c0[32];
 };
 
-// EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in eq.y, all
-// starting from the dense problem-index word eq.word[w], c0 = 0); otherwise word w of found_q.
+// EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in its y field, all
+// starting from the dense problem-index word in its word field, c0 = 0); otherwise word w of found_q.
 template <bool WRITE_PAD, bool KEEP, bool EARLY>
 __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
                                             BsiCounters *ctr, BsiKeep *keep, const BsiEarlyQ &eq,
@@ -793,18 +809,26 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
         u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u, lam_max = 0u;
+        const BsiEarlyEntry ent = bsi_early_entry(eq, EARLY ? w : 0ull);
+        (void)ent;
         // one pass over the 32 records of this word: every field that is needed later goes to
         // (thread-interleaved, hence coalesced) local arrays
         u64 cw_[EARLY ? 1 : 32][BSI_KW], cz_[EARLY ? 1 : 32][BSI_KW], cx_[EARLY ? 1 : 32][BSI_KW];
         if (EARLY) {
-            valid = eq.mask[w];
+            valid = ent.mask[0];
             from_idx = valid;
+            // all 32 queue loads first (independent, in flight together; ncu: one exposed DRAM
+            // latency per lane was a third of this kernel), then the per-lane work
+            u64 lc_[32];
+#pragma unroll
+            for (u32 l = 0; l < 32; ++l) lc_[l] = ((valid >> l) & 1u) ? ent.lamc[l * 32u] : 1ull;
 #pragma unroll 1
             for (u32 l = 0; l < 32; ++l) {
                 if (!((valid >> l) & 1u)) continue;
-                const u64 lc = eq.lamc[l * eq.cap + w];
+                const u64 lc = lc_[l];
                 const u32 lam = (u32)lc, c = (u32)(lc >> 32);
-                const u32 adv = (lam - c % lam) % lam;
+                // (fixed points, the bulk of the ordered regime, need no division)
+                const u32 adv = lam == 1u ? 0u : (lam - c % lam) % lam;
                 aux_s[l * BSI_BLOCK + tid] = adv;
                 adv_max = max(adv_max, adv);
                 c_max = max(c_max, c);
@@ -849,7 +873,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
         if (EARLY) {
-            BSI_LOAD_MEM(b, (eq.y + w), eq.cap)
+            BSI_LOAD_MEM(b, ent.y, 32)
             BSI_UNPACK(keep->key, b)                 // the states as codes: keys of the fixed points
         }
         // (throughput paths) the canonical keys, computed here: no separate pass over the records
@@ -857,7 +881,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         (void)lam_max;
         valid_out = valid;
         if (EARLY) {
-            BSI_LOAD_MEM(b, (eq.y + w), eq.cap)      // (again: the key walk needed the registers)
+            BSI_LOAD_MEM(b, ent.y, 32)      // (again: the key walk needed the registers)
         } else {
             BSI_PACK(b, cw_)
         }
@@ -890,7 +914,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #define BSI_OR_AB(i) a##i |= b##i;
             BSI_FOR_NODES(BSI_COPY_CB)
             if (EARLY) {
-                const u64 W_ = eq.word[w];
+                const u64 W_ = ent.word[0];
                 BSI_INIT_DENSE(a, W_)
                 BSI_PREFIX(BSI_LP_ORIGIN)
             } else {
