@@ -261,15 +261,24 @@ __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
 // Warp-aggregated table update, called by ALL 32 threads of a warp (n == 0: nothing to add).
 // In the ordered regime millions of lanes fall into a handful of attractors: one atomicAdd
 // triple per THREAD then serialises on a few L2 addresses (measured: 2.3 ns per word, the whole
-// resolution time).  Threads holding the same key are summed with shuffles and their first
-// lane adds once; after a few rounds (many distinct keys in the warp: nothing to gain) the
-// remaining threads add for themselves.
+// resolution time).  Threads holding the same key as the first pending thread are summed over
+// the warp (redux on 16-bit pieces: exact, no carries lost) and that thread takes the total; after
+// a few rounds (many distinct keys in the warp: nothing to gain) the others keep their own.  The
+// table is only touched AFTER the rounds, by all the threads that hold a total at once, so the
+// probe latencies overlap instead of adding up round by round.
+__device__ __forceinline__ u64 bsi_warp_sum(u64 x) {
+    const u32 p0 = __reduce_add_sync(0xFFFFFFFFu, (u32)x & 0xFFFFu);
+    const u32 p1 = __reduce_add_sync(0xFFFFFFFFu, (u32)(x >> 16) & 0xFFFFu);
+    const u32 p2 = __reduce_add_sync(0xFFFFFFFFu, (u32)(x >> 32) & 0xFFFFu);
+    const u32 p3 = __reduce_add_sync(0xFFFFFFFFu, (u32)(x >> 48));
+    return (u64)p0 + ((u64)p1 << 16) + ((u64)p2 << 32) + ((u64)p3 << 48);
+}
 __device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slots, const u64 *key, u64 n,
                                                    u64 s1, u64 s2, u32 lam, BsiCounters *ctr) {
     const u32 lane = threadIdx.x & 31u;
     u32 pending = __ballot_sync(0xFFFFFFFFu, n != 0ull);
 #pragma unroll 1
-    for (int round = 0; pending && round < 4; ++round) {
+    for (int round = 0; pending && round < 3; ++round) {
         const u32 leader = __ffs(pending) - 1;
         bool same = n != 0ull;
 #pragma unroll
@@ -278,19 +287,16 @@ __device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slot
             same = same && (k == key[i]);                               //  no short-circuit around it)
         }
         const u32 grp = __ballot_sync(0xFFFFFFFFu, same);
-        u64 a = same ? n : 0ull, b = same ? s1 : 0ull, c = same ? s2 : 0ull;
-        if (grp != (1u << leader)) {
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
-                b += __shfl_xor_sync(0xFFFFFFFFu, b, d);
-                c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-            }
+        if (grp != (1u << leader)) {                                    // (uniform over the warp)
+            const u64 a = bsi_warp_sum(same ? n : 0ull);
+            const u64 b = bsi_warp_sum(same ? s1 : 0ull);
+            const u64 c = bsi_warp_sum(same ? s2 : 0ull);
+            if (lane == leader) { n = a; s1 = b; s2 = c; }
+            else if (same) n = 0ull;                                    // handed over to the leader
         }
-        if (lane == leader) bsi_table_add(table, log2_slots, key, a, b, c, lam, ctr);
         pending &= ~grp;
     }
-    if ((pending >> lane) & 1u) bsi_table_add(table, log2_slots, key, n, s1, s2, lam, ctr);
+    if (n != 0ull) bsi_table_add(table, log2_slots, key, n, s1, s2, lam, ctr);
 }
 
 // perturbation prefix: LP steps from t = 0, perturbations overriding at their time
