@@ -163,11 +163,16 @@ def words_from_code(code, kw):
     return np.array([(code >> (64 * j)) & (2 ** 64 - 1) for j in range(kw)], np.uint64)
 
 
-def states_from_word_rows(rows, n_nodes):
-    """uint64 [n_states, key_words] -> list of n_states lists of n_nodes bools (bit i = node i)."""
+def state_array_from_word_rows(rows, n_nodes):
+    """uint64 [n_states, key_words] -> bool array [n_states, n_nodes] (bit i = node i)."""
     rows = np.ascontiguousarray(rows, dtype='<u8')
     bits = np.unpackbits(rows.view(np.uint8).reshape(rows.shape[0], -1), axis=1, bitorder='little')
-    return bits[:, :n_nodes].astype(bool).tolist()
+    return bits[:, :n_nodes].astype(bool)
+
+
+def states_from_word_rows(rows, n_nodes):
+    """uint64 [n_states, key_words] -> list of n_states lists of n_nodes bools (bit i = node i)."""
+    return state_array_from_word_rows(rows, n_nodes).tolist()
 
 
 def code_from_words(words):

@@ -13,22 +13,69 @@ import io
 import math
 import os
 
+import numpy as np
+
 simulation_name = 'simulation'              # constants.py:45
 aggregated_attractor_name = 'attractor'     # constants.py:46
 
 
-def _state_rows(states, fixed_nodes, perturbed_nodes_by_t, states_id, time_labels):
-    """write_states + format_state (output.py:845-865, 1092-1110)."""
+def _state_rows(states, fixed_nodes, perturbed_nodes_by_t, states_id, time_labels, rows=None):
+    """write_states + format_state (output.py:845-865, 1092-1110), cell by cell."""
     fixed = list(fixed_nodes)
-    rows = []
-    for t, state in enumerate(states):
-        cells = ['1' if v else '0' for v in state]
+    out = []
+    for t in (range(len(states)) if rows is None else rows):
+        cells = ['1' if v else '0' for v in states[t]]
         for node in fixed:
             cells[node] += '_'
         for node in perturbed_nodes_by_t.get(t, ()):
             cells[node] += '*'
-        rows.append([states_id, time_labels[t] if time_labels else str(t)] + cells)
-    return rows
+        out.append([states_id, time_labels[t] if time_labels else str(t)] + cells)
+    return out
+
+
+def _state_rows_text(states, fixed_nodes, perturbed_nodes_by_t, states_id, time_labels):
+    """The same rows as CSV text, without a Python operation per cell: all rows of one trajectory
+    share the positions of commas and `_` markers, so they are one byte matrix (a template row
+    repeated, the 0/1 digits written into it column-wise); only rows with a perturbation marker
+    (`*` changes the row's width) go cell by cell.  Ids, time labels and cells never contain a
+    character that csv.writer would quote, so the text equals what csv.writer produces."""
+    n_rows = len(states)
+    if n_rows == 0:
+        return ''
+    arr = np.asarray(states, dtype=bool)
+    if arr.ndim != 2 or arr.shape[1] == 0:
+        buf = io.StringIO(newline='')
+        csv.writer(buf).writerows(_state_rows(arr.tolist(), fixed_nodes, perturbed_nodes_by_t, states_id, time_labels))
+        return buf.getvalue()
+    n_nodes = arr.shape[1]
+    fixed = set(fixed_nodes)
+    template, digit_at = bytearray(), []
+    for node in range(n_nodes):
+        digit_at.append(len(template))
+        template += b'0_' if node in fixed else b'0'
+        template += b',' if node < n_nodes - 1 else b'\r\n'
+    matrix = np.tile(np.frombuffer(bytes(template), np.uint8), (n_rows, 1))
+    matrix[:, digit_at] = arr.astype(np.uint8) + ord('0')
+    cells = matrix.view('S%d' % len(template)).ravel().tolist()
+    prefix = states_id.encode('ascii') + b','
+    labels = [label.encode('ascii') + b',' for label in time_labels] if time_labels else _plain_labels(n_rows)
+    lines = [prefix + label + row for label, row in zip(labels, cells)]
+    for t in perturbed_nodes_by_t:
+        if 0 <= t < n_rows and perturbed_nodes_by_t[t]:
+            row = _state_rows(arr[t:t + 1].tolist(), fixed_nodes, {0: perturbed_nodes_by_t[t]}, states_id,
+                              [time_labels[t] if time_labels else str(t)])[0]
+            lines[t] = ','.join(row).encode('ascii') + b'\r\n'
+    return b''.join(lines).decode('ascii')
+
+
+_LABELS = []
+
+
+def _plain_labels(n_rows):
+    """[b'0,', b'1,', ...] (cached: every simulation of a run has the same time axis)"""
+    while len(_LABELS) < n_rows:
+        _LABELS.append(b'%d,' % len(_LABELS))
+    return _LABELS[:n_rows]
 
 
 def simulations_csv(db_conn, node_names):
@@ -46,11 +93,15 @@ def simulations_csv(db_conn, node_names):
             for node in perturbed_nodes:
                 n_perturbations_by_node[node] += 1
         sim_id = '{}{}'.format(simulation_name, index + 1)
-        ws.writerow([sim_id, len(simulation.states) - 1] +
+        # (device results carry their states as a bool array; reference records as lists)
+        sim_states = getattr(simulation, 'states_array', None)
+        if sim_states is None:
+            sim_states = simulation.states
+        ws.writerow([sim_id, len(sim_states) - 1] +
                     [int(node in simulation.fixed_nodes) for node in range(n_nodes)] +
                     n_perturbations_by_node)
-        wt.writerows(_state_rows(simulation.states, simulation.fixed_nodes,
-                                 simulation.perturbed_nodes_by_t, sim_id, None))
+        states.write(_state_rows_text(sim_states, simulation.fixed_nodes,
+                                      simulation.perturbed_nodes_by_t, sim_id, None))
     return summaries.getvalue(), states.getvalue()
 
 
@@ -77,7 +128,7 @@ def attractors_csv(db_conn, fixed_nodes, node_names, n_simulation_problems, max_
         ws.writerow([att_id, len(attractor.states), attractor.trajectory_l_mean, sd,
                      attractor.frequency / n_simulation_problems])
         labels = ['t'] + ['t+{}'.format(t) for t in range(1, len(attractor.states))]
-        wt.writerows(_state_rows(attractor.states, fixed_nodes, {}, att_id, labels))
+        states.write(_state_rows_text(attractor.states, fixed_nodes, {}, att_id, labels))
     return summaries.getvalue(), states.getvalue()
 
 

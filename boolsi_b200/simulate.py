@@ -13,17 +13,31 @@ def count_perturbations(perturbed_nodes_by_t):
 
 
 class Simulation:
-    """reference simulate.py:16-28"""
+    """reference simulate.py:16-28.  `states` may be given as a bool array [n_states, n_nodes]
+    (what the device results unpack to): it is kept as `states_array` for the vectorised CSV
+    writer, and `states` -- the reference's list of lists of bool -- is made on first use."""
 
     def __init__(self, states, fixed_nodes, perturbed_nodes_by_t):
-        self.states = states
+        if hasattr(states, 'tolist'):
+            self.states_array = states
+            self._states = None
+        else:
+            self.states_array = None
+            self._states = states
         self.fixed_nodes = fixed_nodes
         self.perturbed_nodes_by_t = perturbed_nodes_by_t
         self.n_perturbations = count_perturbations(perturbed_nodes_by_t)
 
+    @property
+    def states(self):
+        if self._states is None:
+            self._states = self.states_array.tolist()
+        return self._states
+
 
 def states_from_words(rows, n_nodes):
-    return _lib.states_from_word_rows(rows, n_nodes)
+    """-> bool array [n_states, n_nodes]"""
+    return _lib.state_array_from_word_rows(rows, n_nodes)
 
 
 def store_simulations(db_conn, simulations):
@@ -52,8 +66,13 @@ def simulate_master(mpi_comm, n_simulation_problem_batches_per_process, origin_s
     with _lib.Plan(packed, _lib.MODE_SIMULATE, device=device) as plan:
         states, _ = plan.simulate_run(0, packed.n_problems, max_t)
     simulations = []
-    for index in range(packed.n_problems):
-        _, fixed, perturbed = decode_simulation_problem(index, origin_simulation_problem,
-                                                        simulation_problem_variations)
-        simulations.append(Simulation(states_from_words(states[index], n_nodes), fixed, perturbed))
+    chunk = 1024                       # unpack many trajectories per numpy call, bounded memory
+    for begin in range(0, packed.n_problems, chunk):
+        words = states[begin:begin + chunk]
+        bools = states_from_words(words.reshape(-1, words.shape[-1]), n_nodes).reshape(
+            words.shape[0], words.shape[1], n_nodes)
+        for k in range(words.shape[0]):
+            _, fixed, perturbed = decode_simulation_problem(begin + k, origin_simulation_problem,
+                                                            simulation_problem_variations)
+            simulations.append(Simulation(bools[k], fixed, perturbed))
     store_simulations(db_conn, simulations)

@@ -62,3 +62,53 @@ def test_no_attractor_row():
     rows = list(csv.reader(io.StringIO(summaries)))
     assert rows[1] == ['no_attractor', '<= 4', '<= 10', '', '0.625']       # output.py:655-660
     assert rows[2][:2] == ['attractor1', '1'] and float(rows[2][4]) == 3 / 8
+
+
+def test_vectorised_state_rows_equal_the_cell_by_cell_writer():
+    """The byte-matrix formatter against csv.writer over the per-cell rows: random trajectories,
+    fixed-node `_` markers, perturbation `*` markers (incl. on fixed nodes and at t = 0), both
+    label styles, one node, empty trajectory."""
+    import csv
+    import io
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        n_nodes = int(rng.integers(1, 40))
+        n_rows = int(rng.integers(0, 30))
+        states = rng.integers(0, 2, size=(n_rows, n_nodes)).astype(bool).tolist()
+        fixed = {int(i): bool(rng.integers(0, 2)) for i in rng.choice(n_nodes, size=int(rng.integers(0, min(4, n_nodes) + 1)), replace=False)}
+        perturbed = {}
+        for _ in range(int(rng.integers(0, 5))):
+            perturbed.setdefault(int(rng.integers(0, max(n_rows, 1) + 2)), {})[int(rng.integers(0, n_nodes))] = True
+        labels = None if trial % 2 else ['t'] + ['t+%d' % t for t in range(1, n_rows)]
+        want = io.StringIO(newline='')
+        csv.writer(want).writerows(csv_out._state_rows(states, fixed, perturbed, 'simulation%d' % trial, labels))
+        assert csv_out._state_rows_text(states, fixed, perturbed, 'simulation%d' % trial, labels) == want.getvalue()
+
+
+def test_simulation_record_from_a_state_array_equals_the_one_from_lists():
+    """Device results unpack to bool arrays: the record keeps the array for the CSV writer and
+    hands the reference's list-of-lists out on demand; both routes give the same files."""
+    import numpy as np
+    from boolsi_b200 import _lib
+    from boolsi_b200.simulate import Simulation
+    rng = np.random.default_rng(9)
+    words = rng.integers(0, 1 << 63, size=(12, 1), dtype=np.uint64)
+    arr = _lib.state_array_from_word_rows(words, 40)
+    assert arr.shape == (12, 40) and arr.dtype == bool
+    assert arr.tolist() == _lib.states_from_word_rows(words, 40)
+    assert [sum(int(b) << i for i, b in enumerate(row)) for row in arr.tolist()] == \
+        [int(w) & ((1 << 40) - 1) for w in words[:, 0]]
+    fixed, perturbed = {3: True}, {2: {5: False}, 7: {3: True, 0: True}}
+    names = ['n%d' % i for i in range(40)]
+    texts = []
+    for states in (arr, arr.tolist()):
+        db = ResultStore()
+        init_simulation_db_structure(db)
+        db.root.simulations[(0, 0)] = Simulation(states, fixed, perturbed)
+        db.root.simulations[(0, 1)] = Simulation(states[:1], {}, {})
+        assert db.root.simulations[(0, 0)].states == arr.tolist()
+        texts.append(csv_out.simulations_csv(db, names))
+    assert texts[0] == texts[1]
+    assert texts[0][1].count('\r\n') == 1 + 12 + 1
+    assert '1_*' in texts[0][1] or '0_*' in texts[0][1]
