@@ -2,57 +2,76 @@
 target back to itself in the control-flow graph (the cold handlers only ever add instructions),
 with its instruction mix -- LDL/STL on it are register spills paid every iteration.
 usage: python tools/sass_hotpath.py <cubin> <kernel> [min_lop3]"""
-import heapq, re, subprocess, sys
+import heapq
+import re
+import subprocess
+import sys
 from collections import Counter
-out = subprocess.run(['cuobjdump', '-sass', '-fun', sys.argv[2], sys.argv[1]], capture_output=True, text=True).stdout
-minl = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-ins = []
-for l in out.splitlines():
-    m = re.match(r'\s+/\*([0-9a-f]{4,6})\*/\s+(.*?)\s*;', l)
-    if m:
-        ins.append((int(m.group(1), 16), m.group(2)))
-idx = {a: i for i, (a, _) in enumerate(ins)}
-def op(t):
-    return re.sub(r'^@!?U?P\d+\s+', '', t).split()[0].split('.')[0]
-succ = []
-heads = set()
-for i, (a, t) in enumerate(ins):
-    s = []
-    m = re.search(r'\bBRA(?:\.[A-Z]+)*\s+(?:U?P\d+,\s*|UR\d+,\s*|!U?P\d+,\s*)?0x([0-9a-f]+)', t)
-    o = op(t)
-    if m and o == 'BRA':
-        tgt = int(m.group(1), 16)
-        if tgt in idx:
-            s.append(idx[tgt])
-            if tgt < a:
-                heads.add(tgt)
-        if t.startswith('@') or '.DIV' in t or re.search(r'BRA\.U\s+!?UP', t):
-            s.append(i + 1)
-    elif o not in ('EXIT', 'RET'):
-        s.append(i + 1)
-    succ.append([x for x in s if x < len(ins)])
-for h in sorted(heads):
-    src = idx[h]
-    dist = {}; prev = {}
-    pq = [(1, j, src) for j in succ[src]]
-    heapq.heapify(pq)
-    found = None
-    while pq:
-        d, i, p = heapq.heappop(pq)
-        if i in dist:
+
+_BRANCH = re.compile(r'\bBRA(?:\.[A-Z]+)*\s+(?:U?P\d+,\s*|UR\d+,\s*|!U?P\d+,\s*)?0x([0-9a-f]+)')
+
+
+def _op(text):
+    return re.sub(r'^@!?U?P\d+\s+', '', text).split()[0].split('.')[0]
+
+
+def hot_loops(cubin_path, kernel, min_lop3=100):
+    """-> [(loop head address, #instructions on the hot path, Counter of opcodes)] for the loops
+    of `kernel` whose hot path has at least `min_lop3` LOP3."""
+    sass = subprocess.run(['cuobjdump', '-sass', '-fun', kernel, cubin_path], capture_output=True,
+                          text=True, check=True).stdout
+    ins = []
+    for line in sass.splitlines():
+        m = re.match(r'\s+/\*([0-9a-f]{4,6})\*/\s+(.*?)\s*;', line)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2)))
+    index = {address: i for i, (address, _) in enumerate(ins)}
+    successors, heads = [], set()
+    for i, (address, text) in enumerate(ins):
+        nxt = []
+        m = _BRANCH.search(text)
+        opcode = _op(text)
+        if m and opcode == 'BRA':
+            target = int(m.group(1), 16)
+            if target in index:
+                nxt.append(index[target])
+                if target < address:
+                    heads.add(target)
+            if text.startswith('@') or '.DIV' in text or re.search(r'BRA\.U\s+!?UP', text):
+                nxt.append(i + 1)               # conditional: may fall through
+        elif opcode not in ('EXIT', 'RET'):
+            nxt.append(i + 1)
+        successors.append([j for j in nxt if j < len(ins)])
+    loops = []
+    for head in sorted(heads):
+        source = index[head]
+        dist, prev = {}, {}
+        queue = [(1, j, source) for j in successors[source]]
+        heapq.heapify(queue)
+        closed = False
+        while queue:
+            d, i, p = heapq.heappop(queue)
+            if i in dist:
+                continue
+            dist[i], prev[i] = d, p
+            if i == source:
+                closed = True
+                break
+            for j in successors[i]:
+                if j not in dist:
+                    heapq.heappush(queue, (d + 1, j, i))
+        if not closed:
             continue
-        dist[i] = d; prev[i] = p
-        if i == src:
-            found = d; break
-        for j in succ[i]:
-            if j not in dist:
-                heapq.heappush(pq, (d + 1, j, i))
-    if found is None:
-        continue
-    path = []; i = prev[src]
-    while i != src:
-        path.append(ins[i][1]); i = prev[i]
-    path.append(ins[src][1])
-    c = Counter(op(x) for x in path)
-    if c['LOP3'] >= minl:
-        print(hex(h), 'len', len(path), dict(c.most_common(10)))
+        path, i = [ins[source][1]], prev[source]
+        while i != source:
+            path.append(ins[i][1])
+            i = prev[i]
+        mix = Counter(_op(text) for text in path)
+        if mix['LOP3'] >= min_lop3:
+            loops.append((head, len(path), mix))
+    return loops
+
+
+if __name__ == '__main__':
+    for head, length, mix in hot_loops(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 100):
+        print(hex(head), 'len', length, dict(mix.most_common(10)))
