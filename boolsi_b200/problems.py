@@ -52,6 +52,42 @@ def decode_simulation_problem(index, origin_simulation_problem, simulation_probl
     return state, fixed, perturbed
 
 
+class ProblemDecoder:
+    """`fixed_nodes` / `perturbed_nodes_by_t` of many problems of one space, for the `Simulation`
+    records of simulate / target (the initial state is not needed there: it is `states[0]`).
+    Same result as `decode_simulation_problem(index, ...)[1:]`; the radices are worked out once,
+    the initial-state digits are skipped with one division, and a space without fixed-node or
+    perturbation variations hands out one shared pair of (read-only) dicts."""
+
+    def __init__(self, origin_simulation_problem, simulation_problem_variations):
+        _, self.fixed_nodes, self.perturbed_nodes_by_t = origin_simulation_problem
+        var_initial, var_fixed, var_perturbed = simulation_problem_variations
+        self.skip = 1 << len(var_initial)
+        self.var_fixed = [(node, NODE_STATE_BY_DIGIT[range_name(r)], range_radix(r)) for node, r in var_fixed]
+        self.var_perturbed = [(t, node, NODE_STATE_BY_DIGIT[range_name(r)], range_radix(r))
+                              for t, node, r in var_perturbed]
+        self.shared = None
+        if not self.var_fixed and not self.var_perturbed:
+            self.shared = (dict(self.fixed_nodes), {t: dict(nodes) for t, nodes in self.perturbed_nodes_by_t.items()})
+
+    def masks(self, index):
+        """:return: (fixed_nodes dict, perturbed_nodes_by_t dict) of problem `index`"""
+        if self.shared is not None:
+            return self.shared
+        rest = index // self.skip
+        fixed = dict(self.fixed_nodes)
+        for node, values, radix in self.var_fixed:
+            rest, digit = divmod(rest, radix)
+            if values[digit] is not None:
+                fixed[node] = values[digit]
+        perturbed = {t: dict(nodes) for t, nodes in self.perturbed_nodes_by_t.items()}
+        for t, node, values, radix in self.var_perturbed:
+            rest, digit = divmod(rest, radix)
+            if values[digit] is not None:
+                perturbed.setdefault(t, {})[node] = values[digit]
+        return fixed, perturbed
+
+
 def shard_range(n_problems, rank, world):
     """Contiguous, word-aligned (multiple of 32) slice of [0, n_problems) for one GPU."""
     words = (n_problems + 31) // 32

@@ -4,7 +4,7 @@ import logging
 
 from . import _lib
 from .db import init_simulation_db_structure
-from .problems import decode_simulation_problem
+from .problems import ProblemDecoder
 
 
 def count_perturbations(perturbed_nodes_by_t):
@@ -67,12 +67,12 @@ def simulate_master(mpi_comm, n_simulation_problem_batches_per_process, origin_s
         states, _ = plan.simulate_run(0, packed.n_problems, max_t)
     simulations = []
     chunk = 1024                       # unpack many trajectories per numpy call, bounded memory
+    decoder = ProblemDecoder(origin_simulation_problem, simulation_problem_variations)
     for begin in range(0, packed.n_problems, chunk):
         words = states[begin:begin + chunk]
         bools = states_from_words(words.reshape(-1, words.shape[-1]), n_nodes).reshape(
             words.shape[0], words.shape[1], n_nodes)
         for k in range(words.shape[0]):
-            _, fixed, perturbed = decode_simulation_problem(begin + k, origin_simulation_problem,
-                                                            simulation_problem_variations)
+            fixed, perturbed = decoder.masks(begin + k)
             simulations.append(Simulation(bools[k], fixed, perturbed))
     store_simulations(db_conn, simulations)

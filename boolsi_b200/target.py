@@ -4,7 +4,7 @@ from math import inf
 
 from . import _lib
 from .db import init_simulation_db_structure
-from .problems import decode_simulation_problem
+from .problems import ProblemDecoder
 from .simulate import Simulation, states_from_words, store_simulations
 
 
@@ -83,9 +83,9 @@ def target_master(mpi_comm, n_simulation_problem_batches_per_process, origin_sim
             rows, _ = plan.simulate_list([int(hit_index[pos]) for pos in members], t_max)
             for row, pos in zip(rows, members):
                 states_by_pos[pos] = states_from_words(row[:int(hit_t[pos]) + 1], packed.n_nodes)
+        decoder = ProblemDecoder(origin_simulation_problem, simulation_problem_variations)
         for pos, index in enumerate(hit_index):
-            _, fixed, perturbed = decode_simulation_problem(int(index), origin_simulation_problem,
-                                                            simulation_problem_variations)
+            fixed, perturbed = decoder.masks(int(index))
             simulations.append(Simulation(states_by_pos[pos], fixed, perturbed))
     store_simulations(db_conn, simulations)
     log.info('{} simulations reach target state.'.format(db_conn.root.n_simulations()))

@@ -132,3 +132,23 @@ def test_sharded_target_hits_merge_in_enumeration_order(n_to_find):
         assert total == len(want)
         assert [int(i) for i in index] == [int(i) for i in want[:cap]]
         assert [int(x) for x in t] == [int(rec['stop_t'][i]) for i in want[:cap]]
+
+
+def test_problem_decoder_masks_equal_the_full_decode():
+    """ProblemDecoder (what the masters use for the Simulation records) against
+    decode_simulation_problem on every problem of spaces with all NodeStateRange kinds."""
+    from boolsi_b200.constants import NodeStateRange as R
+    from boolsi_b200.problems import ProblemDecoder, count_simulation_problems, decode_simulation_problem
+    origin = ([False, True, False, True, False, False], {4: True}, {3: {1: False}, 7: {0: True}})
+    spaces = [
+        ([0, 2, 5], [], []),
+        ([], [(3, R.MAYBE_TRUE)], [(3, 2, R.MAYBE_TRUE_OR_FALSE)]),
+        ([1, 2], [(3, R.TRUE_OR_FALSE), (5, R.MAYBE_FALSE)], [(3, 1, R.MAYBE_TRUE_OR_FALSE), (9, 0, R.TRUE_OR_FALSE),
+                                                            (7, 0, R.MAYBE_FALSE)]),
+        ([], [], []),
+    ]
+    for variations in spaces:
+        decoder = ProblemDecoder(origin, variations)
+        for index in range(count_simulation_problems(variations)):
+            _, fixed, perturbed = decode_simulation_problem(index, origin, variations)
+            assert decoder.masks(index) == (fixed, perturbed), (variations, index)
