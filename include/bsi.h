@@ -154,8 +154,10 @@ typedef struct bsi_run_stats {
     uint64_t reserved[6];
 } bsi_run_stats;
 
-/* ---- library ----------------------------------------------------------------------------- */
+/* ---- library (no counterpart in the reference: versioning, diagnostics, device discovery) -- */
 int bsi_abi_version(void);
+/* Text of the calling thread's last failure; what the Python wrapper raises, as cli.py:146-149
+ * logs any exception of a run. */
 const char *bsi_last_error(void);
 int bsi_device_count(int *count);
 /* Plans park freed device buffers for reuse by later plans of the same process (and keep
@@ -163,6 +165,10 @@ int bsi_device_count(int *count);
 int bsi_release_cached_memory(void);
 
 /* ---- plan: network + problem space + mode, specialised through NVRTC for one device ------- */
+/* Replaces the per-run set-up of the reference: configure_solve_simulation_problem
+ * (mpi.py:351-376: the mode's per-trajectory function with its caps bound), the fixed-node
+ * rewrite of the rules (model.py:31-49, re-done per batch at mpi.py:525-528) and the numeral
+ * system of the problem space (batching.py:10-46). */
 typedef struct bsi_plan bsi_plan;
 
 int bsi_plan_create(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
@@ -175,12 +181,13 @@ int bsi_plan_create_offline(const bsi_network_desc *network, const bsi_space_des
                             const bsi_target_desc *target, const bsi_plan_opts *opts,
                             bsi_plan **out);
 void bsi_plan_destroy(bsi_plan *plan);
-int bsi_plan_n_problems(const bsi_plan *plan, uint64_t *n);   /* 'total combination count' */
+int bsi_plan_n_problems(const bsi_plan *plan, uint64_t *n);   /* 'total combination count', input.py:124-157 */
 int bsi_plan_key_words(const bsi_plan *plan, uint32_t *kw);
 /* A plan starts on its own non-blocking stream.  cuda_stream: a cudaStream_t / CUstream handle;
  * NULL = the CUDA default (legacy) stream; (void *)-1 = back to the plan's own stream. */
 int bsi_plan_set_stream(bsi_plan *plan, void *cuda_stream);
-/* Generated CUDA source / build log (NUL-terminated, owned by the plan). */
+/* Generated CUDA source / build log (NUL-terminated, owned by the plan; diagnostics, no reference
+ * counterpart). */
 const char *bsi_plan_source(const bsi_plan *plan);
 const char *bsi_plan_build_log(const bsi_plan *plan);
 /* The sm_100a cubin NVRTC produced for the plan's dominant kernel unit (owned by the plan):
@@ -262,7 +269,7 @@ int bsi_target_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_
                    uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,
                    bsi_run_stats *stats);
 
-/* ---- measurement helpers ------------------------------------------------------------------ */
+/* ---- measurement helpers (bench.py's roofline denominators; no reference counterpart) ------ */
 /* Integer-logic roofline microbenchmark: independent LOP3 chains on every SM of `device`;
  * returns thread-level lop3.b32 results per second and the SM clock (MHz) seen during the run. */
 int bsi_measure_lop3_peak(int device, double *lop3_per_s, double *sm_clock_mhz, int *n_sms);
