@@ -11,6 +11,7 @@
 // simulate.py:97-178 (see include/bsi.h for the per-function citations).
 #include <cuda.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -408,6 +409,63 @@ struct CachedUnit {
 std::mutex g_unit_mu;
 std::map<std::pair<std::string, int>, CachedUnit> g_units;
 
+// Optional second level on disk, for the NEXT process that runs the same network (NVRTC takes a
+// few seconds per network, a 2^30-state cambium run 50 ms): off unless BSI_CACHE_DIR names a
+// directory.  One file per unit, named by a hash of (header, template, NVRTC version, unit); the
+// file repeats the header, which is compared on load, so a hash collision cannot hand out the
+// wrong kernels.  Written to a temporary name and renamed: readers never see a partial file.
+uint64_t fnv1a(const std::string &text, uint64_t h = 0xCBF29CE484222325ull) {
+    for (unsigned char c : text) { h ^= c; h *= 0x100000001B3ull; }
+    return h;
+}
+std::string disk_cache_path(const std::string &header, int unit) {
+    const char *dir = getenv("BSI_CACHE_DIR");
+    if (!dir || !*dir) return std::string();
+    int major = 0, minor = 0;
+    nvrtcVersion(&major, &minor);
+    uint64_t h = fnv1a(header);
+    h = fnv1a(bsi_template_src, h);
+    h = fnv1a("nvrtc" + std::to_string(major) + "." + std::to_string(minor) + "/unit" + std::to_string(unit), h);
+    char name[64];
+    snprintf(name, sizeof name, "/bsi-%016llx-u%d.cubin", (unsigned long long)h, unit);
+    return std::string(dir) + name;
+}
+const char kDiskMagic[8] = {'B', 'S', 'I', 'C', 'U', 'B', '1', '\n'};
+bool disk_cache_load(const std::string &path, const std::string &header, CachedUnit *out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    char magic[8];
+    uint64_t n[3];
+    std::string h, log;
+    std::vector<char> cubin;
+    if (fread(magic, 1, 8, f) == 8 && memcmp(magic, kDiskMagic, 8) == 0 && fread(n, 8, 3, f) == 3 &&
+        n[0] == header.size() && n[1] < (1u << 24) && n[2] > 0 && n[2] < (1u << 28)) {
+        h.resize(n[0]);
+        log.resize(n[1]);
+        cubin.resize(n[2]);
+        ok = fread(&h[0], 1, n[0], f) == n[0] && (n[1] == 0 || fread(&log[0], 1, n[1], f) == n[1]) &&
+             fread(cubin.data(), 1, n[2], f) == n[2] && h == header;
+    }
+    fclose(f);
+    if (!ok) return false;
+    out->cubin = std::make_shared<const std::vector<char>>(std::move(cubin));
+    out->log = log;
+    return true;
+}
+void disk_cache_store(const std::string &path, const std::string &header, const CachedUnit &c) {
+    const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                   // an unwritable cache directory is not an error
+    const uint64_t n[3] = {header.size(), c.log.size(), c.cubin->size()};
+    bool ok = fwrite(kDiskMagic, 1, 8, f) == 8 && fwrite(n, 8, 3, f) == 3 &&
+              fwrite(header.data(), 1, n[0], f) == n[0] &&
+              (n[1] == 0 || fwrite(c.log.data(), 1, n[1], f) == n[1]) &&
+              fwrite(c.cubin->data(), 1, n[2], f) == n[2];
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 int compile_plan(bsi_plan *p) {
     StageTimer tm;
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
@@ -462,10 +520,22 @@ int compile_plan(bsi_plan *p) {
                 p->cubins[u] = it->second.cubin;
                 p->unit_key[u] = it->second.key;
                 if (!it->second.log.empty()) p->log += it->second.log + "\n";
-            } else {
-                std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
-                jobs.emplace_back(u, std::async(std::launch::async, compile_unit, std::move(src)));
+                continue;
             }
+            const std::string unit_key = std::to_string(header.size()) + ":" +
+                                         std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(u);
+            const std::string path = disk_cache_path(header, u);
+            CachedUnit from_disk;
+            if (!path.empty() && disk_cache_load(path, header, &from_disk)) {
+                from_disk.key = unit_key;
+                p->cubins[u] = from_disk.cubin;
+                p->unit_key[u] = unit_key;
+                if (!from_disk.log.empty()) p->log += from_disk.log + "\n";
+                g_units[{header, u}] = std::move(from_disk);
+                continue;
+            }
+            std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
+            jobs.emplace_back(u, std::async(std::launch::async, compile_unit, std::move(src)));
         }
     }
     int rc = BSI_OK;
@@ -482,6 +552,8 @@ int compile_plan(bsi_plan *p) {
         if (!c.log.empty()) p->log += c.log + "\n";
         p->cubins[job.first] = c.cubin;
         p->unit_key[job.first] = c.key;
+        const std::string path = disk_cache_path(header, job.first);
+        if (!path.empty()) disk_cache_store(path, header, c);
         std::lock_guard<std::mutex> lk(g_unit_mu);
         if (g_units.size() >= 1024) g_units.clear();
         g_units[{header, job.first}] = std::move(c);

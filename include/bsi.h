@@ -165,6 +165,8 @@ int bsi_device_count(int *count);
 int bsi_release_cached_memory(void);
 
 /* ---- plan: network + problem space + mode, specialised through NVRTC for one device ------- */
+/* Compiled kernels are cached per process.  Environment BSI_CACHE_DIR=<directory> (off when unset)
+ * adds an on-disk level, so that later processes skip the few seconds of NVRTC per network. */
 /* Replaces the per-run set-up of the reference: configure_solve_simulation_problem
  * (mpi.py:351-376: the mode's per-trajectory function with its caps bound), the fixed-node
  * rewrite of the rules (model.py:31-49, re-done per batch at mpi.py:525-528) and the numeral

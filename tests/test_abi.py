@@ -72,3 +72,49 @@ def test_no_gpu_is_an_error_not_a_fallback(built):
     with pytest.raises(_lib.BsiError) as e:
         _lib.Plan(pk, _lib.MODE_ATTRACT, device=0)
     assert e.value.status == -2
+
+
+def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
+    """BSI_CACHE_DIR (off by default): the first process compiles and stores one file per unit,
+    the second one loads them instead of running NVRTC and gets byte-identical kernels; a
+    damaged file is ignored (recompiled), never trusted."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    import time
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, time, hashlib; sys.path.insert(0, %r)\n"
+        "from boolsi_b200 import _lib, synth\n"
+        "cfg = synth.random_attract_problem(24, 3, 5, n_free=10)\n"
+        "pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],\n"
+        "                        cfg['origin simulation problem'], cfg['simulation problem variations'])\n"
+        "t = time.perf_counter()\n"
+        "plan = _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True)\n"
+        "print(time.perf_counter() - t, hashlib.sha1(plan.cubin()).hexdigest(), plan.cubin_bytes())\n" % repo)
+
+    def run(cache_dir):
+        env = dict(os.environ)
+        env.pop('BSI_CACHE_DIR', None)
+        if cache_dir is not None:
+            env['BSI_CACHE_DIR'] = str(cache_dir)
+        out = subprocess.run([sys.executable, '-c', script], env=env, capture_output=True, text=True, check=True)
+        seconds, digest, size = out.stdout.split()
+        return float(seconds), digest, int(size)
+
+    cold = run(tmp_path)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 6 and all(f.startswith('bsi-') and f.endswith('.cubin') for f in files), files
+    warm = run(tmp_path)
+    assert warm[1:] == cold[1:]
+    assert warm[0] < 0.5 * cold[0], (cold, warm)
+    # a truncated file and a file with foreign content fall back to compiling
+    victim = os.path.join(tmp_path, files[0])
+    data = open(victim, 'rb').read()
+    open(victim, 'wb').write(data[:len(data) // 2])
+    open(os.path.join(tmp_path, files[1]), 'wb').write(b'not a cache file')
+    again = run(tmp_path)
+    assert again[1:] == cold[1:]
+    assert open(victim, 'rb').read() == data                      # rewritten after the recompile
+    assert run(None)[1:] == cold[1:]                              # and without the variable: plain NVRTC
