@@ -801,6 +801,9 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
 struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it runs in the same kernel
     u64 key[32][BSI_KW];
     u32 lam[32], c0[32];
+    // early words only: all valid lanes are fixed points (lambda = 1, c0 = 0) holding the SAME
+    // state -- the ordered regime's normal case.  Then only key[first valid lane] is filled.
+    u32 uniform;
 };
 
 // EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in its y field, all
@@ -878,16 +881,41 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
+        bool uniform = false;
+        if (KEEP && !EARLY) keep->uniform = 0u;
         if (EARLY) {
             BSI_LOAD_MEM(b, ent.y, 32)
-            BSI_UNPACK(keep->key, b)                 // the states as codes: keys of the fixed points
+            if (lam_max <= 1u && valid) {
+                // all fixed points: do the valid lanes hold one and the same state?  (two ops per
+                // node instead of the 32x32 transposes and the per-lane key compares)
+                const u32 l0_ = __ffs(valid) - 1;
+                u32 diff_ = 0u;
+                u64 ukey_[BSI_KW];
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) ukey_[i] = 0ull;
+#define BSI_UNI_NODE(i)                                                           \
+    {                                                                             \
+        const u32 r_ = 0u - ((b##i >> l0_) & 1u);                                 \
+        diff_ |= (b##i ^ r_) & valid;                                             \
+        ukey_[(i) >> 6] |= (u64)(r_ & 1u) << ((i) & 63);                          \
+    }
+                BSI_FOR_NODES(BSI_UNI_NODE)
+#undef BSI_UNI_NODE
+                uniform = diff_ == 0u;
+                if (uniform) {
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) keep->key[l0_][i] = ukey_[i];
+                }
+            }
+            if (!uniform) BSI_UNPACK(keep->key, b)   // the states as codes: keys of the fixed points
+            keep->uniform = uniform ? 1u : 0u;
         }
         // (throughput paths) the canonical keys, computed here: no separate pass over the records
         if (KEEP) bsi_key_core(keep->key, valid, lam_max);
         (void)lam_max;
         valid_out = valid;
         if (EARLY) {
-            BSI_LOAD_MEM(b, ent.y, 32)      // (again: the key walk needed the registers)
+            if (!uniform) BSI_LOAD_MEM(b, ent.y, 32)      // (again: the transposes took the registers)
         } else {
             BSI_PACK(b, cw_)
         }
@@ -994,6 +1022,9 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                                                 BsiKeep *keep, u32 lanes) {
     {
         u32 todo = 0u;
+        u64 uni_n = 0, uni_s1 = 0, uni_s2 = 0;
+        u32 uni_l0 = 0u;
+        bool have_uni = false;
         if (FROM_KEEP) {
             // same kernel as the mu walk: keys / lambda / c0 were kept, mu - c0 is in aux_s
             todo = lanes;
@@ -1012,9 +1043,52 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                 }
             }
         }
+        // ---- uniform early word: one key, lambda = 1, c0 = 0 -- no key compares, no group search ---
+        if (FROM_KEEP && todo && keep->uniform) {
+            const u32 l0 = __ffs(todo) - 1;
+            u64 n = 0, s1 = 0, s2 = 0;
+            const bool len_ok = 1ull <= max_attractor_l;          // attract.py:294 with lambda = 1
+#pragma unroll 4
+            for (u32 l = 0; l < 32; ++l) {
+                if (!((todo >> l) & 1u)) continue;
+                const u64 mu = aux_s[l * BSI_BLOCK + threadIdx.x];
+                if (mu + 1ull <= T) {
+                    steps += BSI_LP_ORIGIN + mu + 1ull;
+                    if (len_ok) {
+                        const u64 tl = BSI_LP_ORIGIN + mu;
+                        n += 1; s1 += tl; s2 += tl * tl;
+                    } else {
+                        ++n_rej;
+                    }
+                } else {
+                    steps += stop_t_cap;
+                    ++n_rej;
+                }
+            }
+            n_acc += n;
+            // hand the one group to the common code below: it finds todo == own lanes all "same"
+            // only through key compares, so add here and leave nothing to do
+            if (WARP_AGG) {
+                // (the warp-level add is a collective: it is issued below, once, for every thread)
+                uni_n = n; uni_s1 = s1; uni_s2 = s2; uni_l0 = l0;
+                have_uni = true;
+            } else if (n) {
+                bsi_table_add(table, log2_slots, keep->key[l0], n, s1, s2, 1u, ctr);
+            }
+            todo = 0u;
+        }
         // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
         // (WARP_AGG: every thread of the warp is here, idle ones with todo == 0, and the loop is
         // warp-uniform so that threads holding the same key can be summed before the atomics)
+        if (WARP_AGG) {
+            // the uniform threads' totals first (collective: every thread of the warp takes part)
+            if (__any_sync(0xFFFFFFFFu, have_uni)) {
+                u64 key0[BSI_KW];
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) key0[i] = have_uni ? keep->key[uni_l0][i] : 0ull;
+                bsi_warp_table_add(table, log2_slots, key0, have_uni ? uni_n : 0ull, uni_s1, uni_s2, 1u, ctr);
+            }
+        }
         for (;;) {
             if (WARP_AGG ? !__any_sync(0xFFFFFFFFu, todo != 0u) : !todo) break;
             const u32 l0 = todo ? __ffs(todo) - 1 : 0u;
