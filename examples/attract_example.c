@@ -1,6 +1,6 @@
 /*
- * Plain C against the libbsi C ABI (include/bsi.h): `attract` for the three-node network of the
- * reference's example2 (A* = B, B* = A or C... see below) over all 2^3 initial states.
+ * Plain C against the libbsi C ABI (include/bsi.h): `attract` for a three-node network over all
+ * 2^3 initial states.
  *
  *   gcc -std=c99 -Iinclude examples/attract_example.c -Lboolsi_b200 -lbsi \
  *       -Wl,-rpath,$PWD/boolsi_b200 -o build/attract_example
@@ -10,6 +10,9 @@
  * Network (predecessors sorted ascending, truth-table entry j has the FIRST predecessor as its
  * most significant bit -- reference input.py:796, 881):
  *   node 0:  x0' = x1              node 1:  x1' = x0 AND x2          node 2:  x2' = NOT x2
+ *
+ * Expected (the oracle's answer): 22 trajectory-steps, two attractors of length 2 -- key 0
+ * (states 0, 4) and key 2 (states 2, 5), each with frequency 4 and trajectory lengths summing to 3.
  */
 #include <inttypes.h>
 #include <stdio.h>
