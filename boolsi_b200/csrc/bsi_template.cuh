@@ -467,30 +467,18 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #define BSI_FILT0(X) {}
 #define BSI_FILT1(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u;                                                                 \
-        p0 = ~alive;                                                                 \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        p0 |= q0;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
     }
 #define BSI_FILT2(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u, q1 = 0u;                                                        \
-        p0 = p1 = ~alive;                                                            \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
-        p0 |= q0;                                                                    \
-        p1 |= q1;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
+        BSI_CMP_FILTER1(p1, alive, X, k1_)                                           \
     }
 #define BSI_FILT3(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u, q1 = 0u, q2 = 0u;                                               \
-        p0 = p1 = p2 = ~alive;                                                       \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
-        BSI_CMP_FILTER(p2, q2, X, k2_)                                               \
-        p0 |= q0;                                                                    \
-        p1 |= q1;                                                                    \
-        p2 |= q2;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
+        BSI_CMP_FILTER1(p1, alive, X, k1_)                                           \
+        BSI_CMP_FILTER1(p2, alive, X, k2_)                                           \
     }
 #define BSI_ANY0 false
 #define BSI_ANY1 (p0 != 0xFFFFFFFFu)

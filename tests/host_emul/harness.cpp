@@ -14,7 +14,8 @@
 //                                        each), then the re-packed words
 //   F  alive a_0 .. a_{N-1} k_0 .. k_{N-1}  -> the hot-loop filter of a against checkpoint k:
 //                                        prints p (lanes that cannot match), the reference value
-//                                        computed term by term, and the full-compare mask
+//                                        computed term by term, the full-compare mask, and p
+//                                        again through the single-chain hot-loop macro
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -106,7 +107,9 @@ int main() {
             const u32 ref_filter = ref;
             BSI_FOR_REST(REF)
 #undef REF
-            std::printf("%u %u %u %u", p, ref_filter, full, ref);
+            u32 p1 = 0x12345678u;                       // (whatever it held before is overwritten)
+            BSI_CMP_FILTER1(p1, alive, a, k)
+            std::printf("%u %u %u %u %u", p, ref_filter, full, ref, p1);
         }
         std::printf("\n");
     }

@@ -134,8 +134,8 @@ def test_generated_macros_executed_on_the_host(seed, tmp_path):
             valid = 0xFFFFFFFF if 32 * w[1] + 32 <= pk.n_problems else (1 << (pk.n_problems - 32 * w[1])) - 1
             assert [x & valid for x in g] == [x & valid for x in w[2]], cmd
         elif isinstance(w, tuple) and w[0] == 'filter':
-            p, ref_filter, full, ref_full = g
-            assert p == ref_filter, cmd                     # macro == term-by-term filter
+            p, ref_filter, full, ref_full, p_hot = g
+            assert p == ref_filter == p_hot, cmd            # both macro forms == term-by-term filter
             assert full == ref_full == w[1], cmd            # filter + rest == full compare
             assert p & ~full == 0                           # a filter pass is necessary for a match
         else:
