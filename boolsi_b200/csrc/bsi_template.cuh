@@ -38,9 +38,13 @@ typedef unsigned long long u64;
 
 template <int LUT>
 __device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
+#ifdef BSI_HOST_EMUL        // tests/host_emul: this very template, executed by 32 host threads per warp
+    return bsi_host_lop3(LUT, a, b, c);
+#else
     u32 d;
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return d;
+#endif
 }
 
 #define BSI_MAX_CK 72
@@ -325,7 +329,11 @@ __device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slot
 // per-thread scratch in global memory (sized by the persistent grid) only holds the detection
 // records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32] (the matched states
 // themselves stay in shared memory / in a bit-sliced latch until the end of the word).
+#ifdef BSI_HOST_EMUL
+extern unsigned char bsi_smem[];
+#else
 extern __shared__ __align__(16) unsigned char bsi_smem[];
+#endif
 
 // full compare of a state held in local memory with a checkpoint in shared memory: lanes of
 // `cand` whose N words all agree

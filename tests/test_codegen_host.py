@@ -43,7 +43,7 @@ def _random_network(seed):
 
 
 def _harness(tmp_path, packed):
-    with _lib.Plan(packed, _lib.MODE_ATTRACT, offline=True) as plan:
+    with _lib.Plan(packed, _lib.MODE_ATTRACT, offline=True, source_only=1) as plan:
         header = plan.source().split('#line 1 "bsi_template.cuh"')[0]
     path = tmp_path / 'header.h'
     path.write_text(header)
