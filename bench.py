@@ -241,6 +241,9 @@ def run_gpu(a):
     # e2e: the public call (boolsi_b200.attract.attract_sharded) from HOST structures to HOST
     # results, every step: pack descriptors, create the plan (NVRTC result cached in-process),
     # run, all_gather, read the table back, regenerate the attractor states.
+    # (one untimed call first: the orbit-regeneration and table-export kernels are launched for the
+    # first time in this leg, and the driver loads a kernel's code lazily at its first launch)
+    attract_sharded(*args, max_t=MAX_T, max_attractor_l=inf, device=local, rank=rank, world=world)
     barrier()
     e0 = time.perf_counter()
     e_steps = 0

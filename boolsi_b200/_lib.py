@@ -68,7 +68,8 @@ class PlanOpts(C.Structure):
                 ('keep_source', C.c_uint32), ('block_threads', C.c_uint32),
                 ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
                 ('resolve_few_words', C.c_uint32), ('no_early_words', C.c_uint32),
-                ('smem_slots', C.c_uint32), ('reserved', C.c_uint32 * 5)]
+                ('smem_slots', C.c_uint32), ('source_only', C.c_uint32),
+                ('reserved', C.c_uint32 * 4)]
 
 
 class RunStats(C.Structure):

@@ -504,6 +504,10 @@ int compile_plan(bsi_plan *p) {
                                "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n";
     p->source = header + "\n#line 1 \"bsi_template.cuh\"\n" + bsi_template_src;
     tm.lap("generate source");
+    if (p->opts.source_only) {                             // inspection / host emulation: no NVRTC
+        p->source = "#define BSI_UNIT 0\n" + p->source;
+        return BSI_OK;
+    }
 
     // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
     // thread-safe across programs): the two trajectory kernels dominate the compile time.  Units
@@ -653,6 +657,10 @@ int create_plan(const bsi_network_desc *network, const bsi_space_desc *space, in
         delete p;
         bool unsup = err.find("not supported") != std::string::npos || err.find("unsupported") != std::string::npos;
         return fail(unsup ? BSI_E_UNSUPPORTED : BSI_E_ARG, "%s", err.c_str());
+    }
+    if (p->opts.source_only && device >= 0) {
+        delete p;
+        return fail(BSI_E_ARG, "source_only is for offline plans (bsi_plan_create_offline)");
     }
     int rc = compile_plan(p);
     if (rc == BSI_OK && device >= 0) rc = load_plan(p, device);

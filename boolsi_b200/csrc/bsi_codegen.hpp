@@ -457,6 +457,16 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
             const char *acc = (parity++ & 1) ? "acc2" : "acc";
             o << " " << acc << " = bsi_lop3<0xF6>(" << acc << ", X##" << f << ", Y##" << f << ");";
         }
+        // the hot-loop form: acc = ~ALIVE | OR_f (X_f ^ Y_f) as ONE chain of |filter| lop3 -- the
+        // first one folds the "not alive" term in (0x6F = ~a | (b ^ c)).  The chain is short next
+        // to the ~100 independent lop3 of a step, so a second accumulator (and the two extra
+        // instructions to start and merge it) buys nothing.
+        o << " }\n#define BSI_CMP_FILTER1(acc, ALIVE, X, Y) {";
+        if (filter.empty()) o << " acc = ~(ALIVE);";
+        for (size_t g = 0; g < filter.size(); ++g) {
+            if (g == 0) o << " acc = bsi_lop3<0x6F>(ALIVE, X##" << filter[g] << ", Y##" << filter[g] << ");";
+            else o << " acc = bsi_lop3<0xF6>(acc, X##" << filter[g] << ", Y##" << filter[g] << ");";
+        }
         o << " }\n#define BSI_CMP_REST(acc, X, Y) {";
         for (int i = 0; i < n; ++i)
             if (!in_filter[i]) o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", Y##" << i << ");";

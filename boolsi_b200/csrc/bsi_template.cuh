@@ -11,21 +11,25 @@
 // The reference stops a trajectory at the first repeated state, t = mu + lambda (relative to the
 // last perturbation time lp), provided that is <= T = max_t - lp.  Here, store-free:
 //
-//   bsi_attract_main   one forward pass per word with up to three live CHECKPOINTS.  A lane whose
-//       state equals a checkpoint taken at time c is on its cycle, c >= mu, and because every
-//       later state is compared the first such match is at time c + lambda: lambda is exact.
-//       Checkpoint times for a horizon H: powers of two while they are < H/3 (early detection,
-//       Brent style, all in slot 0), then ceil(H/3), ceil(2H/3), H in slots 0, 1, 2.  A lane with
-//       c_(i-1) < mu <= c_i and mu + lambda <= H is matched by time c_i + lambda < H + gap, so
-//       running to H + max gap - 1 PROVES "mu + lambda > H" for every lane still unmatched.
-//       The per-step compare is a FILTER over a few nodes held in registers; only when some lane
+//   bsi_attract_dense / bsi_attract_queue   one forward pass per word (dense: a contiguous index
+//       range; queue: the lanes a previous round left open) with up to three live CHECKPOINTS.  A
+//       lane whose state equals a checkpoint taken at time c is on its cycle, c >= mu, and because
+//       every later state is compared the first such match is at time c + lambda: lambda is exact.
+//       Checkpoint times for a horizon H: 0, 1, 2, 3, 4, 6, 8, 12, 16, 24, ... while they are below
+//       ceil(H/3) (early detection, Brent style, all in slot 0), then ceil(H/3), ceil(2H/3), H in
+//       slots 0, 1, 2.  A lane with c_(i-1) < mu <= c_i and mu + lambda <= H is matched by time
+//       c_i + lambda < H + gap, so running to H + max gap - 1 PROVES "mu + lambda > H" for every
+//       lane still unmatched (tests/test_schedule.py checks the obligation by brute force).
+//       The per-step compare is a FILTER over a dozen nodes held in registers; only when some lane
 //       passes the filter (and a second filter over a dozen more words) is the full state
-//       compared against the checkpoint, which is kept in shared memory.
-//   bsi_resolve_key    canonical key = minimum state code over the cycle (model.py:140-149,
-//       attract.py:296) by a bit-sliced lexicographic-minimum walk of the cycle.
-//   bsi_resolve_mu     exact mu by walking x_j (from the previous checkpoint, whose time is
-//       provably < mu, or from the problem index) in lock-step with the periodic extension of
-//       the cycle; then acceptance (mu + lambda <= T, lambda <=
+//       compared against the checkpoint, which is kept in shared memory.  Lanes matched against
+//       an early checkpoint leave bit-sliced through the early-word queue, the others as
+//       48-byte records in the found queue, open lanes as indices in the retry queue.
+//   bsi_resolve_mu, bsi_resolve_early (long queues), bsi_resolve + bsi_resolve_finish (short ones)
+//       canonical key = minimum state code over the cycle (model.py:140-149, attract.py:296) by a
+//       bit-sliced lexicographic-minimum walk of the cycle; exact mu by walking x_j (from the
+//       previous checkpoint, whose time is provably < mu, or from the problem index) in lock-step
+//       with the periodic extension of the cycle; then acceptance (mu + lambda <= T, lambda <=
 //       max_attractor_l, attract.py:294) and aggregation into the device attractor table.
 
 typedef unsigned char u8;
@@ -34,9 +38,13 @@ typedef unsigned long long u64;
 
 template <int LUT>
 __device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
+#ifdef BSI_HOST_EMUL        // tests/host_emul: this very template, executed by 32 host threads per warp
+    return bsi_host_lop3(LUT, a, b, c);
+#else
     u32 d;
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return d;
+#endif
 }
 
 #define BSI_MAX_CK 72
@@ -321,7 +329,11 @@ __device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slot
 // per-thread scratch in global memory (sized by the persistent grid) only holds the detection
 // records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32] (the matched states
 // themselves stay in shared memory / in a bit-sliced latch until the end of the word).
+#ifdef BSI_HOST_EMUL
+extern unsigned char bsi_smem[];
+#else
 extern __shared__ __align__(16) unsigned char bsi_smem[];
+#endif
 
 // full compare of a state held in local memory with a checkpoint in shared memory: lanes of
 // `cand` whose N words all agree
@@ -463,30 +475,18 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #define BSI_FILT0(X) {}
 #define BSI_FILT1(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u;                                                                 \
-        p0 = ~alive;                                                                 \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        p0 |= q0;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
     }
 #define BSI_FILT2(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u, q1 = 0u;                                                        \
-        p0 = p1 = ~alive;                                                            \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
-        p0 |= q0;                                                                    \
-        p1 |= q1;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
+        BSI_CMP_FILTER1(p1, alive, X, k1_)                                           \
     }
 #define BSI_FILT3(X)                                                                 \
     {                                                                                \
-        u32 q0 = 0u, q1 = 0u, q2 = 0u;                                               \
-        p0 = p1 = p2 = ~alive;                                                       \
-        BSI_CMP_FILTER(p0, q0, X, k0_)                                               \
-        BSI_CMP_FILTER(p1, q1, X, k1_)                                               \
-        BSI_CMP_FILTER(p2, q2, X, k2_)                                               \
-        p0 |= q0;                                                                    \
-        p1 |= q1;                                                                    \
-        p2 |= q2;                                                                    \
+        BSI_CMP_FILTER1(p0, alive, X, k0_)                                           \
+        BSI_CMP_FILTER1(p1, alive, X, k1_)                                           \
+        BSI_CMP_FILTER1(p2, alive, X, k2_)                                           \
     }
 #define BSI_ANY0 false
 #define BSI_ANY1 (p0 != 0xFFFFFFFFu)

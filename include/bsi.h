@@ -126,7 +126,9 @@ typedef struct bsi_plan_opts {
     uint32_t smem_slots;       /* attract: how many of the three checkpoint slots live in shared memory
                                   (the others in the thread's L2-resident scratch); 0 = auto (3).
                                   2 with min_blocks 6 buys a third warp per scheduler at N = 64 */
-    uint32_t reserved[5];
+    uint32_t source_only;      /* offline plans only: 1 = generate the specialised source (bsi_plan_source,
+                                  bsi_plan_op_counts) and skip NVRTC; the plan has no cubin */
+    uint32_t reserved[4];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */

@@ -77,3 +77,20 @@ def test_python_and_c_oracles_agree_on_a_fresh_network():
     table = coracle.attract_table(rec, sp.kw)
     assert {k: v[:3] for k, v in res['table'].items()} == {k: v[:3] for k, v in table.items()}
     assert res['steps'] == rec['steps']
+
+
+@pytest.mark.parametrize('n_nodes,k,seed,max_t', [(200, 2, 0, 300), (256, 2, 1, 400)])
+def test_python_and_c_oracles_agree_at_the_maximum_network_size(n_nodes, k, seed, max_t):
+    """Four key words per state (129..256 nodes): what tools/next_round/test_gpu_large.py
+    will check the GPU path against (fixtures stop at 128 nodes)."""
+    from boolsi_b200 import synth
+    cfg = synth.random_attract_problem(n_nodes, k, seed, n_free=5)
+    preds, tts = cfg['incoming node lists'], cfg['truth tables']
+    origin, variations = cfg['origin simulation problem'], cfg['simulation problem variations']
+    res = oracle.attract(preds, tts, origin, variations, max_t, inf)
+    sp = coracle.Space(preds, tts, origin, variations)
+    assert sp.kw == 4
+    rec = coracle.attract_records(sp, max_t, inf)
+    table = coracle.attract_table(rec, sp.kw)
+    assert {key: v[:3] for key, v in res['table'].items()} == {key: v[:3] for key, v in table.items()}
+    assert res['steps'] == rec['steps']

@@ -1,0 +1,139 @@
+"""CPU: the attract kernels themselves -- the text of csrc/bsi_template.cuh, not a restatement --
+executed by 32 host threads per warp (tests/host_emul: a small CUDA shim + the launch sequence of
+csrc/bsi.cpp) and compared with the C oracle: attractor table, trajectory-step count, conservation.
+
+What this covers without a GPU: the checkpoint schedule and the three-level match filter, early /
+deferred match records, the early-word queue, retry rounds, key / mu resolution in both the
+latency and the throughput form, warp-aggregated table updates, and the plan options that move
+checkpoints between shared memory and scratch.  What it cannot cover: anything that depends on
+the real memory system or scheduler (that is what the -m gpu tests are for)."""
+import itertools
+import os
+import shutil
+import subprocess
+from math import inf
+
+import numpy as np
+import pytest
+
+from boolsi_b200 import _lib, synth
+from oracle import coracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+pytestmark = pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+
+
+def _build(tmp_path, packed, **opts):
+    with _lib.Plan(packed, _lib.MODE_ATTRACT, offline=True, block_threads=32, source_only=1, **opts) as plan:
+        header = plan.source().split('#line 1 "bsi_template.cuh"')[0]
+    (tmp_path / 'header.h').write_text(header)
+    exe = str(tmp_path / 'kernel_emul')
+    libdir = os.path.join(REPO, 'boolsi_b200')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-w', '-pthread',
+                    '-DBSI_HEADER="%s"' % (tmp_path / 'header.h'),
+                    '-DBSI_TEMPLATE="%s"' % os.path.join(libdir, 'csrc', 'bsi_template.cuh'),
+                    '-I', os.path.join(HERE, 'host_emul'), os.path.join(HERE, 'host_emul', 'kernel_emul.cpp'),
+                    '-L', libdir, '-lbsi', '-Wl,-rpath,' + libdir, '-o', exe], check=True)
+    return exe
+
+
+def _run(exe, lo, hi, max_t, max_a, first_horizon=0, few_words=0, no_early=0, table_log2=12):
+    cap = lambda x: 0 if x == inf else int(x)            # noqa: E731  (0 = no cap on the command line)
+    out = subprocess.run([exe] + [str(int(v)) for v in (lo, hi, cap(max_t), cap(max_a), first_horizon, few_words,
+                                                         no_early, table_log2)],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.splitlines()
+    head = out[0].split()
+    counters = dict(steps=int(head[1]), accepted=int(head[2]), without=int(head[3]), table_full=int(head[4]),
+                    internal_error=int(head[5]))
+    rows = []
+    for line in out[1:]:
+        key_part, stat_part = line[4:].split('|')
+        key = sum(int(w) << (64 * j) for j, w in enumerate(key_part.split()))
+        n, s1, s2, lam = (int(x) for x in stat_part.split())
+        rows.append((key, n, s1, s2, lam))
+    return counters, sorted(rows)
+
+
+def _oracle(space, max_t, max_a, lo, hi):
+    rec = coracle.attract_records(space, max_t, max_a, lo, hi)
+    rows = sorted((k, v[0], v[1], v[2], v[3]) for k, v in coracle.attract_table(rec, space.kw).items())
+    return rows, rec['steps'], int((rec['found'] == 0).sum())
+
+
+def _check(exe, space, lo, hi, max_t, max_a, **run_opts):
+    want_rows, want_steps, want_without = _oracle(space, max_t, max_a, lo, hi)
+    counters, rows = _run(exe, lo, hi, max_t, max_a, **run_opts)
+    assert counters['table_full'] == 0 and counters['internal_error'] == 0
+    assert rows == want_rows, run_opts
+    assert counters['steps'] == want_steps, run_opts
+    assert counters['without'] == want_without
+    assert counters['accepted'] + counters['without'] == hi - lo
+
+
+def _random_case(seed):
+    rng = np.random.default_rng([seed, 31])
+    n = int(rng.integers(2, 41)) if seed % 3 else int(rng.integers(60, 75))
+    preds, tts = [], []
+    for _ in range(n):
+        k = min(int(rng.choice([0, 1, 1, 2, 2, 3, 3, 3, 4, 5, 6])), n)
+        p = sorted(int(x) for x in rng.choice(n, size=k, replace=False))
+        bits = rng.integers(0, 2, size=2 ** k)
+        preds.append(p)
+        tts.append({key: bool(bits[j]) for j, key in enumerate(itertools.product((False, True), repeat=k))})
+    initial = [bool(b) for b in rng.integers(0, 2, size=n)]
+    nodes = [int(x) for x in rng.permutation(n)]
+    n_free = int(rng.integers(1, min(n, 9) + 1))
+    free = sorted(nodes[:n_free])
+    fixed = {node: bool(rng.integers(0, 2)) for node in nodes[n_free:n_free + int(rng.integers(0, 3))]}
+    pert = {}
+    for _ in range(int(rng.integers(0, 4))):
+        pert.setdefault(int(rng.integers(1, 12)), {})[int(rng.integers(0, n))] = bool(rng.integers(0, 2))
+    return (preds, tts, (initial, fixed, pert), (free, [], [])), rng
+
+
+@pytest.mark.parametrize('seed', range(7))
+def test_emulated_kernels_on_random_networks(seed, tmp_path):
+    """Mixed in-degrees 0..6, fixed nodes, perturbations, caps, sub-ranges; every run form: default,
+    tiny first horizon (retry rounds through the queue kernel), throughput-mode resolution,
+    per-lane records only."""
+    args, rng = _random_case(seed)
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk, filter_nodes=[0, 3][seed % 2])
+    max_t = [inf, int(rng.integers(1, 40)), int(rng.integers(40, 400))][seed % 3]
+    max_a = [inf, inf, int(rng.integers(1, 6))][(seed // 3) % 3]
+    n = pk.n_problems
+    lo = int(rng.integers(0, n))
+    hi = int(rng.integers(lo, n + 1))
+    _check(exe, space, 0, n, max_t, max_a)
+    _check(exe, space, lo, hi, max_t, max_a, first_horizon=[1, 2, 7][seed % 3])
+    _check(exe, space, 0, n, max_t, max_a, few_words=1, first_horizon=5)
+    _check(exe, space, lo, hi, max_t, max_a, few_words=1, no_early=1)
+
+
+@pytest.mark.parametrize('opts', [dict(smem_slots=2), dict(smem_slots=1), dict(smem_slots=2, min_blocks=6)],
+                         ids=['slots2', 'slots1', 'slots2-cap168'])
+def test_emulated_kernels_with_checkpoints_in_scratch(opts, tmp_path):
+    cfg = synth.random_attract_problem(64, 3, 1, n_free=9)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk, **opts)
+    _check(exe, space, 0, pk.n_problems, 1000, inf)
+    _check(exe, space, 3, 300, 120, inf, first_horizon=16, few_words=1)
+
+
+@pytest.mark.parametrize('n_nodes,k,seed,max_t', [(160, 2, 3, 300), (256, 2, 1, 400)])
+def test_emulated_kernels_at_the_maximum_network_size(n_nodes, k, seed, max_t, tmp_path):
+    """Three and four key words per state: beyond the golden fixtures (128 nodes)."""
+    cfg = synth.random_attract_problem(n_nodes, k, seed, n_free=7)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    assert pk.kw == (n_nodes + 63) // 64
+    exe = _build(tmp_path, pk)
+    _check(exe, space, 0, pk.n_problems, max_t, inf)
+    _check(exe, space, 5, 100, max_t, inf, few_words=1, first_horizon=8)
