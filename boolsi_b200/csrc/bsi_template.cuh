@@ -1066,10 +1066,9 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                 }
             }
             n_acc += n;
-            // hand the one group to the common code below: it finds todo == own lanes all "same"
-            // only through key compares, so add here and leave nothing to do
+            // the word is one group: nothing is left for the group search below.  The warp-level
+            // add is a collective, so it is issued after this block, once, by every thread.
             if (WARP_AGG) {
-                // (the warp-level add is a collective: it is issued below, once, for every thread)
                 uni_n = n; uni_s1 = s1; uni_s2 = s2; uni_l0 = l0;
                 have_uni = true;
             } else if (n) {

@@ -137,3 +137,18 @@ def test_emulated_kernels_at_the_maximum_network_size(n_nodes, k, seed, max_t, t
     exe = _build(tmp_path, pk)
     _check(exe, space, 0, pk.n_problems, max_t, inf)
     _check(exe, space, 5, 100, max_t, inf, few_words=1, first_horizon=8)
+
+
+@pytest.mark.parametrize('k,seed', [(2, 0), (2, 1), (1, 0)])
+def test_emulated_kernels_in_the_ordered_regime(k, seed, tmp_path):
+    """Every lane falls into one of one or two fixed points within a few steps: whole words hold
+    one key (the uniform early-word path), in both resolution forms and on ragged ranges."""
+    cfg = synth.random_attract_problem(64, k, seed, n_free=11)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk)
+    for max_t, max_a in ((inf, inf), (1000, inf), (6, inf), (inf, 1)):
+        _check(exe, space, 0, pk.n_problems, max_t, max_a, few_words=1)
+        _check(exe, space, 37, 1501, max_t, max_a)
