@@ -152,3 +152,73 @@ def test_emulated_kernels_in_the_ordered_regime(k, seed, tmp_path):
     for max_t, max_a in ((inf, inf), (1000, inf), (6, inf), (inf, 1)):
         _check(exe, space, 0, pk.n_problems, max_t, max_a, few_words=1)
         _check(exe, space, 37, 1501, max_t, max_a)
+
+
+# ---- simulate: bsi_trajectories with per-lane fixed-node / perturbation variations -------------------
+
+def _build_simulate(tmp_path, packed):
+    with _lib.Plan(packed, _lib.MODE_SIMULATE, offline=True, block_threads=32, source_only=1) as plan:
+        header = plan.source().split('#line 1 "bsi_template.cuh"')[0]
+    (tmp_path / 'header_sim.h').write_text(header)
+    exe = str(tmp_path / 'simulate_emul')
+    libdir = os.path.join(REPO, 'boolsi_b200')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-w', '-pthread',
+                    '-DBSI_HEADER="%s"' % (tmp_path / 'header_sim.h'),
+                    '-DBSI_TEMPLATE="%s"' % os.path.join(libdir, 'csrc', 'bsi_template.cuh'),
+                    '-I', os.path.join(HERE, 'host_emul'), os.path.join(HERE, 'host_emul', 'simulate_emul.cpp'),
+                    '-o', exe], check=True)
+    return exe
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_emulated_trajectories_with_every_kind_of_variation(seed, tmp_path):
+    """simulate mode: initial-state, fixed-node and perturbation variations of every NodeStateRange
+    (radix-2 and radix-3 digits, per-lane masks, per-lane last perturbation time) against the C
+    oracle's plain iteration; contiguous ranges and explicit index lists."""
+    from boolsi_b200.constants import NodeStateRange as R
+    ranges = [R.TRUE_OR_FALSE, R.MAYBE_FALSE, R.MAYBE_TRUE, R.MAYBE_TRUE_OR_FALSE]
+    args, rng = _random_case(seed + 50)
+    preds, tts, origin, variations = args
+    n_nodes = len(preds)
+    free = variations[0][:5]
+    others = [i for i in range(n_nodes) if i not in free and i not in origin[1]]
+    var_fixed = [(int(node), ranges[int(rng.integers(0, 4))]) for node in others[:int(rng.integers(0, 3))]]
+    var_pert = [(int(rng.integers(1, 10)), int(rng.integers(0, n_nodes)), ranges[int(rng.integers(0, 4))])
+                for _ in range(int(rng.integers(0, 3)))]
+    args = (preds, tts, origin, (free, var_fixed, var_pert))
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    assert pk.n_problems == space.n_problems
+    exe = _build_simulate(tmp_path, pk)
+    max_t = 14 + seed
+    n = pk.n_problems
+    lo = int(rng.integers(0, n))
+    hi = int(rng.integers(lo, n + 1))
+    for b, e in ((0, n), (lo, hi)):
+        out = tmp_path / 'states.bin'
+        subprocess.run([exe, str(b), str(e), str(max_t), str(out)], check=True, timeout=600)
+        got = np.fromfile(out, dtype='<u8').reshape(e - b, max_t + 1, pk.kw)
+        want, _, _ = coracle.simulate_states(space, max_t, b, e)
+        assert np.array_equal(got, np.asarray(want, np.uint64)), (b, e)
+    pick = sorted(int(i) for i in rng.choice(n, size=min(n, 9), replace=False))
+    out = tmp_path / 'list.bin'
+    subprocess.run([exe, '--list', str(max_t), str(out)] + [str(i) for i in pick], check=True, timeout=600)
+    got = np.fromfile(out, dtype='<u8').reshape(len(pick), max_t + 1, pk.kw)
+    for row, index in zip(got, pick):
+        want, _, _ = coracle.simulate_states(space, max_t, index, index + 1)
+        assert np.array_equal(row, np.asarray(want, np.uint64)[0]), index
+
+
+def test_emulated_trajectories_of_a_256_node_network(tmp_path):
+    cfg = synth.random_attract_problem(256, 3, 2, n_free=6)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    assert pk.kw == 4
+    exe = _build_simulate(tmp_path, pk)
+    out = tmp_path / 'states.bin'
+    subprocess.run([exe, '0', str(pk.n_problems), '40', str(out)], check=True, timeout=600)
+    got = np.fromfile(out, dtype='<u8').reshape(pk.n_problems, 41, 4)
+    want, _, _ = coracle.simulate_states(space, 40, 0, pk.n_problems)
+    assert np.array_equal(got, np.asarray(want, np.uint64))
