@@ -222,3 +222,51 @@ def test_emulated_trajectories_of_a_256_node_network(tmp_path):
     got = np.fromfile(out, dtype='<u8').reshape(pk.n_problems, 41, 4)
     want, _, _ = coracle.simulate_states(space, 40, 0, pk.n_problems)
     assert np.array_equal(got, np.asarray(want, np.uint64))
+
+
+# ---- target: bsi_target_main with horizon rounds and the closure test --------------------------------
+
+@pytest.mark.parametrize('seed', range(6))
+def test_emulated_target_search(seed, tmp_path):
+    """target mode with variations of every kind: first hit time per problem from its own last
+    perturbation on, capped and uncapped (closure rounds), whole space and a ragged sub-range."""
+    from boolsi_b200.constants import NodeStateRange as R
+    ranges = [R.TRUE_OR_FALSE, R.MAYBE_FALSE, R.MAYBE_TRUE, R.MAYBE_TRUE_OR_FALSE]
+    args, rng = _random_case(seed + 80)
+    preds, tts, origin, variations = args
+    n_nodes = len(preds)
+    free = variations[0][:6]
+    others = [i for i in range(n_nodes) if i not in free and i not in origin[1]]
+    var_fixed = [(int(node), ranges[int(rng.integers(0, 4))]) for node in others[:int(rng.integers(0, 3))]]
+    var_pert = [(int(rng.integers(1, 10)), int(rng.integers(0, n_nodes)), ranges[int(rng.integers(0, 4))])
+                for _ in range(int(rng.integers(0, 3)))]
+    args = (preds, tts, origin, (free, var_fixed, var_pert))
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    target_nodes = sorted(int(x) for x in rng.choice(n_nodes, size=int(rng.integers(1, min(n_nodes, 4) + 1)),
+                                                     replace=False))
+    target_code = sum((1 << node) for node in target_nodes if rng.integers(0, 2))
+    tgt = _lib.make_target(set(target_nodes), target_code, pk.kw)
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt, offline=True, block_threads=32, source_only=1) as plan:
+        header = plan.source().split('#line 1 "bsi_template.cuh"')[0]
+    (tmp_path / 'header_tgt.h').write_text(header)
+    exe = str(tmp_path / 'target_emul')
+    libdir = os.path.join(REPO, 'boolsi_b200')
+    subprocess.run(['g++', '-O1', '-std=c++17', '-w', '-pthread',
+                    '-DBSI_HEADER="%s"' % (tmp_path / 'header_tgt.h'),
+                    '-DBSI_TEMPLATE="%s"' % os.path.join(libdir, 'csrc', 'bsi_template.cuh'),
+                    '-I', os.path.join(HERE, 'host_emul'), os.path.join(HERE, 'host_emul', 'target_emul.cpp'),
+                    '-o', exe], check=True)
+    n = pk.n_problems
+    lo = int(rng.integers(0, n))
+    hi = int(rng.integers(lo, n + 1))
+    lp_max = max([t for t in origin[2]] + [t for t, _, _ in var_pert] + [0])
+    for max_t in (inf, lp_max + int(rng.integers(0, 40))):
+        for b, e in ((0, n), (lo, hi)):
+            rec = coracle.target_records(space, set(target_nodes), target_code, max_t, b, e)
+            want = [(b + int(i), int(rec['stop_t'][i])) for i in np.nonzero(rec['reached'])[0]]
+            out = subprocess.run([exe, str(b), str(e), '0' if max_t == inf else str(max_t)], capture_output=True,
+                                 text=True, check=True, timeout=600).stdout.splitlines()
+            got = [tuple(int(x) for x in line.split()[1:]) for line in out if line.startswith('hit')]
+            assert got == want, (max_t, b, e)
+            assert int(out[-1].split()[1]) == len(want)
