@@ -2,7 +2,8 @@
 C oracle -- attract, simulate, target.
 
 Written after round 1's GPU time was spent: the plans specialise offline (NVRTC) and the two
-oracles agree at this size (tests/test_coracle_golden.py), but these tests have NOT run on a GPU
+oracles agree at this size (tests/test_coracle_golden.py), and the host emulation of the kernels
+passes at 160 and 256 nodes (tests/test_kernel_emul.py), but these tests have NOT run on a GPU
 yet, so they live here and not under tests/.  Next round: run
 `python -m pytest tools/next_round/test_gpu_large.py -m gpu -q -p no:cacheprovider` on a B200 (from the
 repo root, so that tests/conftest.py is not needed: the marker below is registered here), fix what
