@@ -270,3 +270,25 @@ def test_emulated_target_search(seed, tmp_path):
             got = [tuple(int(x) for x in line.split()[1:]) for line in out if line.startswith('hit')]
             assert got == want, (max_t, b, e)
             assert int(out[-1].split()[1]) == len(want)
+
+
+@pytest.mark.parametrize('run_opts', [dict(few_words=1), dict(few_words=1, no_early=1), {}],
+                         ids=['throughput', 'throughput-records', 'auto'])
+def test_emulated_kernels_with_thousands_of_attractors(run_opts, tmp_path):
+    """Every node keeps its state except a few on short cycles: 2560 different attractors, every
+    thread of a warp holding many keys at once (the warp-level aggregation falls back to per-thread
+    table updates; the table fills to a fifth)."""
+    n, n_free = 20, 10
+    preds = [[i] for i in range(n)]
+    tts = [{(False,): False, (True,): True} for _ in range(n)]
+    preds[17], preds[18], preds[19] = [18], [19], [17]                   # 17 <- 18 <- 19 <- not 17
+    tts[19] = {(False,): True, (True,): False}
+    preds[16], tts[16] = [3, 16], {(False, False): False, (False, True): True, (True, False): True,
+                                   (True, True): False}
+    args = (preds, tts, ([False] * n, {}, {}), (list(range(n_free)) + [17, 19], [], []))
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk)
+    want_rows, _, _ = _oracle(space, 50, inf, 0, pk.n_problems)
+    assert len(want_rows) == 2560
+    _check(exe, space, 0, pk.n_problems, 50, inf, table_log2=14, **run_opts)
