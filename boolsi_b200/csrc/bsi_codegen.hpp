@@ -470,8 +470,14 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         o << " }\n#define BSI_CMP_REST(acc, X, Y) {";
         for (int i = 0; i < n; ++i)
             if (!in_filter[i]) o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", Y##" << i << ");";
-        o << " }\n#define BSI_CMP_FILTER2_MEM(acc, X, P, S) {";
-        for (size_t g = 0; g < filter2.size(); ++g)
+        // stage 2 in two tiers: a register-filter pass is almost always ONE lane that differs from
+        // the checkpoint elsewhere, and four more words rule it out 15 times out of 16
+        const size_t tier_a = std::min<size_t>(4, filter2.size());
+        o << " }\n#define BSI_CMP_FILTER2A_MEM(acc, X, P, S) {";
+        for (size_t g = 0; g < tier_a; ++g)
+            o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
+        o << " }\n#define BSI_CMP_FILTER2B_MEM(acc, X, P, S) {";
+        for (size_t g = tier_a; g < filter2.size(); ++g)
             o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
         for (int i = 0; i < n; ++i) o << " (P)[" << i << " * (S)] = X##" << i << ";";

@@ -469,7 +469,10 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     if (ACC != 0xFFFFFFFFu) {                                                        \
         BSI_COUNT(0)                                                                 \
         const u32 *p2_ = BSI_CK_PTR(S);                                              \
-        BSI_CMP_FILTER2_MEM(ACC, X, p2_, BSI_CK_STRIDE(S))                           \
+        BSI_CMP_FILTER2A_MEM(ACC, X, p2_, BSI_CK_STRIDE(S))                          \
+        if (ACC != 0xFFFFFFFFu) {                                                    \
+            BSI_CMP_FILTER2B_MEM(ACC, X, p2_, BSI_CK_STRIDE(S))                      \
+        }                                                                            \
     }
             // register filters of state X against the armed slots: p_s = lanes that CANNOT match
 #define BSI_FILT0(X) {}
