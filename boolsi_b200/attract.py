@@ -133,10 +133,27 @@ def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_si
     aggregated_attractor_keys_by_batch_index, the counters), same return value.
 
     `mpi_comm`, the batch count, `packing_db` and `output_dirpath` are accepted and ignored (no
-    task farm, no DB packing, no progress file).  `storing_all_states` is ignored too: results
-    follow the default detection mode (SURVEY.md section 7.2 documents where `-r` differs).
+    task farm, no DB packing, no progress file).
+
+    `storing_all_states=False` (`boolsi attract -r`, reference attract.py:305-371): detection by
+    reference points is a memory-saving device of the CPU implementation, not a different result --
+    without a time cap it reports exactly the attractors, frequencies and trajectory lengths of the
+    default mode, and that is what this path returns (the device path stores no states in either
+    mode).  With a finite `max_t` the reference's `-r` mode additionally needs the repeat to be
+    DETECTED at a reference point by `max_t` and otherwise derives a pseudo-attractor from
+    `max_t - last_reference_t` without checking that a repeat occurred (SURVEY.md section 7.2;
+    tests/golden/rmode.json lists reference-generated cases of both kinds).  Those cap artefacts are
+    not reproduced: a warning says so.
     """
     log = logging.getLogger()
+    if not storing_all_states:
+        if max_t is None or max_t == inf:
+            log.info('-r: reference-point detection and the default detection report the same '
+                     'attractors when there is no time cap; the GPU path stores no states in either mode.')
+        else:
+            log.warning('-r with a time cap (-t {}): results follow the DEFAULT detection mode (an attractor '
+                        'counts when it is reached and closed by max_t); the reference\'s -r mode differs '
+                        'for trajectories whose repeat is not detected at a reference point by max_t.'.format(max_t))
     log.info('GPU path will be used to find attractors from {} initial conditions...'.format(
         n_simulation_problems))
     if not hasattr(db_conn.root, 'aggregated_attractors'):
