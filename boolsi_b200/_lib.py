@@ -34,7 +34,8 @@ EXPORTS = [
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
     'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
     'bsi_attractor_states_batch', 'bsi_attract_schedule', 'bsi_attract_run_async',
-    'bsi_attract_run_finish',
+    'bsi_attract_run_finish', 'bsi_group_create', 'bsi_group_destroy', 'bsi_group_size', 'bsi_group_plan',
+    'bsi_group_attract_run', 'bsi_group_target_run', 'bsi_group_simulate_run', 'bsi_attractor_activity',
 ]
 
 
@@ -65,11 +66,11 @@ class TargetDesc(C.Structure):
 class PlanOpts(C.Structure):
     _fields_ = [('first_horizon', C.c_uint32), ('filter_nodes', C.c_uint32),
                 ('table_log2_slots', C.c_uint32), ('chunk_log2', C.c_uint32),
-                ('keep_source', C.c_uint32), ('block_threads', C.c_uint32),
+                ('no_dict', C.c_uint32), ('block_threads', C.c_uint32),
                 ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
                 ('resolve_few_words', C.c_uint32), ('no_early_words', C.c_uint32),
-                ('smem_slots', C.c_uint32), ('source_only', C.c_uint32),
-                ('reserved', C.c_uint32 * 4)]
+                ('smem_slots', C.c_uint32), ('source_only', C.c_uint32), ('keep_dict', C.c_uint32),
+                ('reserved', C.c_uint32 * 3)]
 
 
 class RunStats(C.Structure):
@@ -134,6 +135,7 @@ def lib():
         L.bsi_attract_table_export_payload.argtypes = [p, p, u64]
         L.bsi_attractor_states.argtypes = [p, p, u64, p]
         L.bsi_attractor_states_batch.argtypes = [p, p, u64, u64, p]
+        L.bsi_attractor_activity.argtypes = [p, p, p, u64, p]
         L.bsi_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_simulate_list.argtypes = [p, p, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_target_run.argtypes = [p, u64, u64, u64, p, p, u64, C.POINTER(u64),
@@ -142,6 +144,15 @@ def lib():
                                             C.POINTER(i)]
         L.bsi_measure_update_rate.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.bsi_attract_schedule.argtypes = [u64, p, p, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.bsi_group_create.argtypes = [C.POINTER(NetworkDesc), C.POINTER(SpaceDesc), i, C.POINTER(TargetDesc),
+                                       C.POINTER(PlanOpts), C.POINTER(i), i, C.POINTER(p)]
+        L.bsi_group_destroy.argtypes = [p]
+        L.bsi_group_destroy.restype = None
+        L.bsi_group_size.argtypes = [p, C.POINTER(i)]
+        L.bsi_group_plan.argtypes = [p, i, C.POINTER(p)]
+        L.bsi_group_attract_run.argtypes = [p, u64, u64, u64, u64, C.POINTER(RunStats), C.POINTER(RunStats)]
+        L.bsi_group_target_run.argtypes = [p, u64, u64, u64, p, p, u64, C.POINTER(u64), C.POINTER(RunStats)]
+        L.bsi_group_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
         _lib = L
     return _lib
 
@@ -263,6 +274,15 @@ def make_target(target_node_set, target_substate_code, kw):
     return t
 
 
+def plan_opts(opts):
+    o = PlanOpts()
+    for k, v in opts.items():
+        if not hasattr(o, k) or k == 'reserved':
+            raise TypeError('unknown plan option %r' % k)
+        setattr(o, k, int(v))
+    return o
+
+
 class Plan:
     """Owner of one `bsi_plan*` (network + problem space + mode specialised for one device)."""
 
@@ -271,11 +291,8 @@ class Plan:
         self.mode = mode
         self.kw = packed.kw
         self._h = C.c_void_p()
-        o = PlanOpts()
-        for k, v in opts.items():
-            if not hasattr(o, k):
-                raise TypeError('unknown plan option %r' % k)
-            setattr(o, k, int(v))
+        self._owned = True
+        o = plan_opts(opts)
         tptr = C.byref(target) if target is not None else None
         if offline:
             check(lib().bsi_plan_create_offline(C.byref(packed.network), C.byref(packed.space),
@@ -284,10 +301,18 @@ class Plan:
             check(lib().bsi_plan_create(C.byref(packed.network), C.byref(packed.space), mode, tptr,
                                         C.byref(o), int(device), C.byref(self._h)))
 
+    @classmethod
+    def borrowed(cls, handle, packed, mode):
+        """A view of a plan that something else owns (a group member): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.packed, self.mode, self.kw = packed, mode, packed.kw
+        self._h, self._owned = handle, False
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             lib().bsi_plan_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -426,6 +451,19 @@ class Plan:
                 out[pos] = buf[row, :lam].copy() if as_words else [code_from_words(w) for w in buf[row, :lam]]
         return out
 
+    def attractor_activity(self, keys_and_lams):
+        """[(key, lam), ...] -> uint64 array [n, n_nodes]: in how many states of each cycle every node
+        is on (attractor_analysis.py:49-51 divides by the cycle length), counted on the device."""
+        n = len(keys_and_lams)
+        counts = np.zeros((n, self.packed.n_nodes), np.uint64)
+        if n:
+            keys = np.zeros((n, self.kw), np.uint64)
+            for row, (key, _) in enumerate(keys_and_lams):
+                keys[row] = words_from_code(int(key), self.kw)
+            lams = np.array([int(lam) for _, lam in keys_and_lams], np.uint64)
+            check(lib().bsi_attractor_activity(self._h, _ptr(keys), _ptr(lams), n, _ptr(counts)))
+        return counts
+
     # ---- simulate / target -----------------------------------------------------------------
     def simulate_run(self, idx_begin, idx_end, max_t):
         n = int(idx_end) - int(idx_begin)
@@ -454,6 +492,76 @@ class Plan:
                                    _ptr(hit_index), _ptr(hit_t), capacity, C.byref(got),
                                    C.byref(st)))
         return hit_index[:got.value], hit_t[:got.value], st.as_dict()
+
+
+class Group:
+    """Owner of one `bsi_group*`: one plan per device in this process; the run functions split the
+    index range over the devices (the replacement of the MPI task farm, reference mpi.py:193-340)."""
+
+    def __init__(self, packed, mode, devices=None, target=None, **opts):
+        self.packed, self.mode, self.kw = packed, mode, packed.kw
+        self._h = C.c_void_p()
+        o = plan_opts(opts)
+        tptr = C.byref(target) if target is not None else None
+        if devices is None:
+            arr, n = None, 0                      # every visible device
+        else:
+            devices = [int(d) for d in devices]
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        check(lib().bsi_group_create(C.byref(packed.network), C.byref(packed.space), mode, tptr, C.byref(o),
+                                     arr, n, C.byref(self._h)))
+        size = C.c_int()
+        check(lib().bsi_group_size(self._h, C.byref(size)))
+        self.n_devices = size.value
+
+    def close(self):
+        if self._h:
+            lib().bsi_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def plan(self, i=0):
+        h = C.c_void_p()
+        check(lib().bsi_group_plan(self._h, int(i), C.byref(h)))
+        return Plan.borrowed(h, self.packed, self.mode)
+
+    def attract_run(self, idx_begin, idx_end, max_t=inf, max_attractor_l=inf):
+        """-> (totals, [per-device stats]); afterwards `plan(0)` holds the whole job's table."""
+        total = RunStats()
+        per = (RunStats * self.n_devices)()
+        check(lib().bsi_group_attract_run(self._h, int(idx_begin), int(idx_end), cap(max_t), cap(max_attractor_l),
+                                          C.byref(total), per))
+        return total.as_dict(), [s.as_dict() for s in per]
+
+    def target_run(self, idx_begin, idx_end, max_t=inf, n_to_find=inf):
+        n = int(idx_end) - int(idx_begin)
+        capacity = n if n_to_find is None or n_to_find == inf else min(n, int(n_to_find))
+        hit_index = np.zeros(max(capacity, 1), np.uint64)
+        hit_t = np.zeros(max(capacity, 1), np.uint64)
+        got = C.c_uint64()
+        st = RunStats()
+        check(lib().bsi_group_target_run(self._h, int(idx_begin), int(idx_end), cap(max_t), _ptr(hit_index),
+                                         _ptr(hit_t), capacity, C.byref(got), C.byref(st)))
+        return hit_index[:got.value], hit_t[:got.value], st.as_dict()
+
+    def simulate_run(self, idx_begin, idx_end, max_t):
+        n = int(idx_end) - int(idx_begin)
+        out = np.zeros((max(n, 1), int(max_t) + 1, self.kw), np.uint64)
+        st = RunStats()
+        check(lib().bsi_group_simulate_run(self._h, int(idx_begin), int(idx_end), int(max_t), _ptr(out),
+                                           C.byref(st)))
+        return out[:n], st.as_dict()
 
 
 def attract_schedule(horizon):

@@ -18,9 +18,18 @@ from scipy import stats
 
 def node_activity(attractors):
     """-> (observations [n_attractors, N] float64, frequencies [n_attractors] int64)
-    (attractor_analysis.py:45-54)."""
-    observations = np.array([np.asarray(a.states, dtype=np.float64).mean(axis=0) for a in attractors])
+    (attractor_analysis.py:45-54).  Attractors that come off the GPU path carry `node_on_counts` -- per
+    node, the number of cycle states in which it is on, counted on the device -- and the observation
+    matrix is ONE array division (counts / cycle length: the same float64 values as the reference's
+    `np.mean(states, axis=0)`, a sum of 0/1 divided by the length); anything else falls back to the
+    states."""
     frequencies = np.array([a.frequency for a in attractors], dtype=np.int64)
+    counts = [getattr(a, 'node_on_counts', None) for a in attractors]
+    if attractors and all(c is not None for c in counts):
+        lengths = np.array([len(a.states) for a in attractors], dtype=np.float64)
+        observations = np.asarray(counts, dtype=np.float64) / lengths[:, None]
+    else:
+        observations = np.array([np.asarray(a.states, dtype=np.float64).mean(axis=0) for a in attractors])
     return observations, frequencies
 
 

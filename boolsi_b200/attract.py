@@ -1,11 +1,15 @@
 """`attract` mode on the GPU path: the drop-in for reference `attract_master` (attract.py:67-230).
 
 Same arguments in, same `db_conn.root.*` post-conditions out; between them the
-work is done by libbsi (bit-sliced CUDA kernels), sharded over the ranks of a
-`torch.distributed` job when there is one -- the replacement for the MPI task farm (mpi.py) -- with
-the per-GPU attractor tables merged by one NCCL all_gather.
+work is done by libbsi (bit-sliced CUDA kernels).  Two ways to use several GPUs, both replacing the
+MPI task farm (mpi.py):
+  * ONE process (what `attract_master` does): a library group, one plan per visible GPU, one host
+    thread each; the peers' export kernels write their tables into GPU 0's memory, one merge launch;
+  * one process PER GPU under `torch.distributed` (`attract_sharded` with world > 1, what bench.py
+    runs under torchrun): per-GPU tables merged by one NCCL all_gather.
 """
 import logging
+from collections import OrderedDict
 from fractions import Fraction
 from math import inf
 
@@ -22,10 +26,13 @@ class AggregatedAttractor:
     `states` (min-code state first, cycle order), `frequency`, `trajectory_l_mean`,
     `trajectory_l_variation_sum` -- the last two derived from the exact integer triple."""
 
-    def __init__(self, key, states, frequency, sum_l, sum_l2):
+    def __init__(self, key, states, frequency, sum_l, sum_l2, node_on_counts=None):
         self.key = key
         self.states = states
         self.frequency = frequency
+        # in how many states of the cycle each node is on, counted on the device (the input of the
+        # node-correlation analysis, attractor_analysis.py:49-51), or None
+        self.node_on_counts = node_on_counts
         self.sum_l, self.sum_l2 = sum_l, sum_l2
         self.trajectory_l_mean = float(Fraction(sum_l, frequency))
         self.trajectory_l_variation_sum = float(Fraction(sum_l2) - Fraction(sum_l * sum_l, frequency))
@@ -90,24 +97,77 @@ class AttractEngine:
                 'n_without': int(headers[:, 3].sum())}
 
     def attractors(self):
-        """-> list of AggregatedAttractor in the reference's output order (attract.py:170-186:
-        frequency descending, then key ascending), states regenerated as the orbit of the key."""
-        n_nodes = self.packed.n_nodes
-        rows = []
-        for r in self.plan.table_read():
-            rows.append((_lib.code_from_words(r['key'][:self.plan.kw]), int(r['n']), int(r['sum_l']),
-                         int(r['sum_l2']), int(r['lam'])))
-        rows.sort(key=lambda x: (-x[1], x[0]))
-        orbits = self.plan.attractor_states_batch([(key, lam) for key, _, _, _, lam in rows], as_words=True)
-        return [AggregatedAttractor(key, _lib.states_from_word_rows(words, n_nodes), n, s1, s2)
-                for (key, n, s1, s2, lam), words in zip(rows, orbits)]
+        """-> list of AggregatedAttractor in the reference's output order."""
+        return read_attractors(self.plan, self.packed.n_nodes)
+
+
+_GROUPS = OrderedDict()          # (descriptor bytes, mode, devices, options) -> _lib.Group, most recent last
+_GROUPS_MAX = 2
+
+
+def cached_group(packed, mode, devices=None, target=None, **plan_opts):
+    """The group (one plan per device) for this network / problem space, kept across calls: a second
+    job on the same input skips kernel specialisation, module loading and buffer allocation -- the
+    per-run set-up the reference repeats per batch (mpi.py:351-376, 525-528).  At most two groups
+    stay alive; `release_cached_plans()` drops them."""
+    key = (tuple((name, a.tobytes()) for name, a in sorted(packed.arrays.items())), mode,
+           None if devices is None else tuple(int(d) for d in devices),
+           None if target is None else bytes(target), tuple(sorted(plan_opts.items())))
+    group = _GROUPS.pop(key, None)
+    if group is None:
+        group = _lib.Group(packed, mode, devices=devices, target=target, **plan_opts)
+        while len(_GROUPS) >= _GROUPS_MAX:
+            _GROUPS.popitem(last=False)[1].close()
+    _GROUPS[key] = group
+    return group
+
+
+def release_cached_plans():
+    while _GROUPS:
+        _GROUPS.popitem()[1].close()
+    _lib.release_cached_memory()
+
+
+def read_attractors(plan, n_nodes):
+    """Table of `plan` -> list of AggregatedAttractor in the reference's output order (attract.py:170-186:
+    frequency descending, then key ascending), states = the orbit of the key, key first."""
+    rows = [(_lib.code_from_words(r['key'][:plan.kw]), int(r['n']), int(r['sum_l']), int(r['sum_l2']), int(r['lam']))
+            for r in plan.table_read()]
+    rows.sort(key=lambda x: (-x[1], x[0]))
+    orbits = plan.attractor_states_batch([(key, lam) for key, _, _, _, lam in rows], as_words=True)
+    counts = plan.attractor_activity([(key, lam) for key, _, _, _, lam in rows])
+    return [AggregatedAttractor(key, _lib.states_from_word_rows(words, n_nodes), n, s1, s2, on)
+            for (key, n, s1, s2, lam), words, on in zip(rows, orbits, counts)]
+
+
+def attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                    simulation_problem_variations, max_t=inf, max_attractor_l=inf, devices=None, **plan_opts):
+    """Host structures in, host results out, ONE process: the index space is split over `devices`
+    (None = every visible GPU) by the library's group run; no torch, no launcher.
+    :return: dict with the sorted attractors and the job totals."""
+    packed = _lib.PackedProblem(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                                simulation_problem_variations)
+    group = cached_group(packed, _lib.MODE_ATTRACT, devices, **plan_opts)
+    total, per_device = group.attract_run(0, packed.n_problems, max_t, max_attractor_l)
+    plan = group.plan(0)
+    attractors = read_attractors(plan, packed.n_nodes)
+    h2d = sum(a.nbytes for a in packed.arrays.values()) + 8 * plan.kw * len(attractors)
+    d2h = 64 * len(attractors) + sum(8 * plan.kw * len(a.states) for a in attractors) + 128 * group.n_devices
+    return {'attractors': attractors, 'n_attractors': len(attractors), 'n_found': total['n_found'],
+            'n_without': total['n_without'], 'steps_total': total['steps'], 'h2d_bytes': h2d,
+            'd2h_bytes': d2h, 'n_devices': group.n_devices, 'stats': total, 'per_device': per_device}
 
 
 def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_problem,
                     simulation_problem_variations, max_t=inf, max_attractor_l=inf, device=0, rank=0,
                     world=1, **plan_opts):
-    """Host structures in, host results out: the whole `attract` job on this rank's GPU (and its
-    peers when `world > 1`).  :return: dict with the sorted attractors and the job totals."""
+    """One rank of a `torch.distributed` job (one process per GPU, e.g. under torchrun): this rank's
+    slice on its GPU, tables merged over NCCL.  With `world == 1` it is `attract_devices` on one GPU.
+    :return: dict with the sorted attractors and the job totals."""
+    if world == 1:
+        return attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                               simulation_problem_variations, max_t, max_attractor_l, devices=[device],
+                               **plan_opts)
     eng = AttractEngine(predecessor_node_lists, truth_tables, origin_simulation_problem,
                         simulation_problem_variations, device=device, rank=rank, world=world,
                         **plan_opts)
@@ -127,13 +187,16 @@ def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_prob
 def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_simulation_problem,
                    simulation_problem_variations, predecessor_node_lists, truth_tables, max_t,
                    max_attractor_l, n_simulation_problems, storing_all_states, db_conn, packing_db,
-                   output_dirpath, device=0):
+                   output_dirpath, devices=None, device=None):
     """Drop-in for reference `attract_master` (attract.py:67-230): same positional arguments, same
     post-conditions on `db_conn.root` (aggregated_attractors keyed `(-frequency, key)`,
     aggregated_attractor_keys_by_batch_index, the counters), same return value.
 
     `mpi_comm`, the batch count, `packing_db` and `output_dirpath` are accepted and ignored (no
-    task farm, no DB packing, no progress file).
+    task farm, no DB packing, no progress file).  Where the reference fans the batches out over the
+    MPI ranks it was started with (mpi.py:193-340), this call splits the index space over every
+    visible GPU from this one process (`devices`: a list of device numbers to restrict it to;
+    `device`: shorthand for one).
 
     `storing_all_states=False` (`boolsi attract -r`, reference attract.py:305-371): detection by
     reference points is a memory-saving device of the CPU implementation, not a different result --
@@ -158,8 +221,11 @@ def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_si
         n_simulation_problems))
     if not hasattr(db_conn.root, 'aggregated_attractors'):
         init_attractor_db_structure(db_conn)
-    res = attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_problem,
-                          simulation_problem_variations, max_t, max_attractor_l, device=device)
+    if device is not None:
+        devices = [device]
+    res = attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                          simulation_problem_variations, max_t, max_attractor_l, devices=devices)
+    log.info('Used {} GPU(s).'.format(res['n_devices']))
     root = db_conn.root
     keys = []
     for a in res['attractors']:

@@ -19,10 +19,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <future>
+#include <map>
 #include <mutex>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bsi_codegen.hpp"
@@ -66,7 +69,8 @@ struct StageTimer {
     X(cuMemcpyHtoDAsync) X(cuMemcpyDtoDAsync) X(cuStreamSynchronize) X(cuStreamCreate)            \
     X(cuStreamDestroy) X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize)                    \
     X(cuEventElapsedTime) X(cuEventDestroy) X(cuGetErrorString) X(cuMemAllocHost)                 \
-    X(cuMemFreeHost)
+    X(cuMemFreeHost) X(cuDeviceCanAccessPeer) X(cuCtxEnablePeerAccess) X(cuMemcpyPeerAsync)       \
+    X(cuStreamWaitEvent)
 
 struct CuApi {
 #define X(name) decltype(&name) p_##name = nullptr;
@@ -123,6 +127,14 @@ struct Sched {
     uint32_t ck_time[kMaxCk];
     uint32_t ck_slot[kMaxCk];
 };
+
+// cycle dictionary (see bsi_template.cuh): kernel parameter, passed by value
+struct DictParam {
+    CUdeviceptr slots, orbit, n_states, n_attr, dir;
+    uint32_t log2_slots, cap_states, cap_attr, pad;
+};
+constexpr uint32_t kDictLog2States = 18;          // orbit storage: 2^18 states, hash slots: twice that
+constexpr uint32_t kDictCapAttr = 1u << 14;
 
 // Checkpoint schedule for horizon H >= 1 (see the header comment of bsi_template.cuh).
 Sched make_sched(uint64_t H) {
@@ -193,13 +205,16 @@ struct bsi_plan {
     CUstream own_stream = nullptr, stream = nullptr;
     CUfunction f_dense = nullptr, f_queue = nullptr, f_mu = nullptr, f_early = nullptr,
                f_resolve = nullptr, f_finish = nullptr,
-               f_export = nullptr, f_merge = nullptr, f_traj = nullptr, f_target = nullptr;
+               f_export = nullptr, f_merge = nullptr, f_merge_payloads = nullptr, f_traj = nullptr, f_counts = nullptr,
+               f_target = nullptr;
     int n_sms = 0;
     int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
     size_t main_smem = 0;
     int smem_slots = 3;
     uint32_t table_log2 = 20;
-    DevBuf ctr, table, found_q, retry_q[2], scratch, early_q, misc, misc2, misc3;
+    DevBuf ctr, table, found_q, retry_q[2], scratch, early_q, misc, misc2, misc3, misc4, misc5;
+    DevBuf dict_slots, dict_orbit, dict_dir, dict_ctr;     // cycle dictionary (attract)
+    DictParam dict{};
     std::vector<CUevent> events;
     size_t events_used = 0;
     uint64_t launches = 0;
@@ -607,6 +622,7 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
     p->stream = p->own_stream;
     CU_CHECK(cuModuleGetFunction(&p->f_traj, p->mods[4], "bsi_trajectories"));
+    CU_CHECK(cuModuleGetFunction(&p->f_counts, p->mods[4], "bsi_orbit_counts"));
     if (p->m.mode == BSI_MODE_ATTRACT) {
         CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mods[1], "bsi_attract_dense"));
         CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
@@ -616,6 +632,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
+        CU_CHECK(cuModuleGetFunction(&p->f_merge_payloads, p->mods[4], "bsi_table_merge_payloads"));
         p->main_smem = (size_t)p->smem_slots * p->m.n * p->block * 4;      // the checkpoint slots held on chip
         if (p->main_smem > 48 * 1024) {
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
@@ -635,6 +652,18 @@ int load_plan(bsi_plan *p, int device) {
         int rc = ensure(p, p->table, slot_bytes << p->table_log2);
         if (rc) return rc;
         CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
+        if (!p->opts.no_dict) {
+            const size_t dslot_bytes = (16 + 8 * (size_t)p->m.kw + 15) / 16 * 16;
+            const uint32_t log2_states = kDictLog2States;
+            if ((rc = ensure(p, p->dict_slots, dslot_bytes << (log2_states + 1))) ||
+                (rc = ensure(p, p->dict_orbit, ((size_t)8 * p->m.kw) << log2_states)) ||
+                (rc = ensure(p, p->dict_dir, (size_t)8 * kDictCapAttr)) || (rc = ensure(p, p->dict_ctr, 256)))
+                return rc;
+            p->dict = DictParam{p->dict_slots.p, p->dict_orbit.p, p->dict_ctr.p, p->dict_ctr.p + 8, p->dict_dir.p,
+                                log2_states + 1, 1u << log2_states, kDictCapAttr, 0};
+            CU_CHECK(cuMemsetD8Async(p->dict_slots.p, 0, dslot_bytes << (log2_states + 1), p->stream));
+            CU_CHECK(cuMemsetD8Async(p->dict_ctr.p, 0, 256, p->stream));
+        }
     }
     if (p->m.mode == BSI_MODE_TARGET) CU_CHECK(cuModuleGetFunction(&p->f_target, p->mods[4], "bsi_target_main"));
     int rc = ensure(p, p->ctr, sizeof(Counters));
@@ -735,7 +764,8 @@ void bsi_plan_destroy(bsi_plan *p) {
             CtxGuard g(p);
             if (p->stream) cu().p_cuStreamSynchronize(p->stream);
             for (DevBuf *b : {&p->ctr, &p->table, &p->found_q, &p->retry_q[0], &p->retry_q[1], &p->scratch,
-                              &p->early_q, &p->misc, &p->misc2, &p->misc3})
+                              &p->early_q, &p->misc, &p->misc2, &p->misc3, &p->misc4, &p->misc5, &p->dict_slots, &p->dict_orbit,
+                              &p->dict_dir, &p->dict_ctr})
                 give_back(p->device, *b);
             tm.lap("destroy: buffers");
             for (CUevent e : p->events) cu().p_cuEventDestroy(e);
@@ -901,12 +931,14 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
     CU_CHECK(cuEventRecord(tm.e0, p->stream));
 
+    // the found queue is sized once for the largest chunk: growing it between chunks would hand a
+    // buffer that earlier kernels may still be writing to back to the pool
+    if ((rc = ensure(p, p->found_q, found_bytes * (std::min(chunk, idx_end - idx_begin) + 64)))) return rc;
     // chunks are aligned to word boundaries (32 problems)
     uint64_t b = idx_begin;
     while (b < idx_end) {
         uint64_t e = std::min(idx_end, ((b >> 5) << 5) + chunk);
         uint64_t n_lanes = e - b;
-        if ((rc = ensure(p, p->found_q, found_bytes * (n_lanes + 32)))) return rc;
         uint64_t H = p->opts.first_horizon ? p->opts.first_horizon : 1024;
         H = std::min(H, kMaxH);
         int which = 0;
@@ -957,7 +989,7 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                 uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
                 uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
                 void *args_m[] = {&p->found_q.p, &n_found_p, &few, &t_rel, &cap_l, &stop_cap, &p->table.p,
-                                  &p->table_log2, &p->ctr.p};
+                                  &p->table_log2, &p->ctr.p, &p->dict};
                 unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
                 uint64_t early_cap = 0;
@@ -967,11 +999,11 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                     early_p = p->early_q.p;
                     CUdeviceptr n_early_p = p->ctr.p + offsetof(Counters, n_early);
                     void *args_e[] = {&early_p, &early_cap, &n_early_p, &n_found_p, &few, &t_rel, &cap_l,
-                                      &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p};
+                                      &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};
                     if ((rc = launch(p, p->f_early, grid_m, p->block, 0, args_e))) return rc;
                 }
                 void *args_r[] = {&p->found_q.p, &n_found_p, &few, &early_p, &early_cap, &t_rel, &cap_l,
-                                  &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p};
+                                  &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};
                 if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
                 if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_r))) return rc;
                 if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;
@@ -1064,15 +1096,21 @@ int bsi_attract_table_clear(bsi_plan *p) {
     // asynchronous on the plan's stream (every later call is ordered after it)
     CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
     CU_CHECK(cuMemsetD8Async(p->ctr.p + offsetof(Counters, table_full), 0, 8, p->stream));
+    // the cycle dictionary goes with the table: a cleared plan has learnt nothing (keep_dict: it stays,
+    // the dictionary only holds facts about the network's dynamics)
+    if (p->dict.slots && !p->opts.keep_dict) {
+        CU_CHECK(cuMemsetD8Async(p->dict_slots.p, 0, p->dict_slots.bytes, p->stream));
+        CU_CHECK(cuMemsetD8Async(p->dict_ctr.p, 0, 256, p->stream));
+    }
     return BSI_OK;
 }
 
 static int export_table(bsi_plan *p, CUdeviceptr out, uint64_t cap, uint64_t *n, CUdeviceptr header,
-                        bool sync) {
+                        bool sync, bool zero_fill = true) {
     int rc = ensure(p, p->misc, 256);
     if (rc) return rc;
     CU_CHECK(cuMemsetD8Async(p->misc.p, 0, 16, p->stream));     // [0] record count, [1] blocks done
-    if (out && cap) CU_CHECK(cuMemsetD8Async(out, 0, cap * sizeof(bsi_attractor_rec), p->stream));
+    if (out && cap && zero_fill) CU_CHECK(cuMemsetD8Async(out, 0, cap * sizeof(bsi_attractor_rec), p->stream));
     CUdeviceptr done = p->misc.p + 8;
     void *args[] = {&p->table.p, &p->table_log2, &out, &cap, &p->misc.p, &header, &p->ctr.p, &done};
     if ((rc = launch(p, p->f_export, (unsigned)(p->n_sms * 4), 256, 0, args))) return rc;
@@ -1150,7 +1188,8 @@ int bsi_attract_table_merge_device(bsi_plan *p, const void *dev_records, uint64_
 // ---- trajectories (simulate, orbits) --------------------------------------------------------------
 static int run_trajectories(bsi_plan *p, uint64_t idx_begin, const uint64_t *indices,
                             const uint64_t *codes, uint64_t n, uint64_t n_steps, uint64_t *out,
-                            bsi_run_stats *stats) {
+                            bsi_run_stats *stats,
+                            const std::function<int(uint64_t, uint64_t)> &after_chunk = nullptr) {
     int rc;
     const uint64_t kw = (uint64_t)p->m.kw;
     if (n_steps >= ((uint64_t)1 << 40)) return fail(BSI_E_ARG, "max_t too large for an explicit trajectory");
@@ -1181,7 +1220,9 @@ static int run_trajectories(bsi_plan *p, uint64_t idx_begin, const uint64_t *ind
         void *args[] = {&first, &d_idx, &d_codes, &m, &n_steps, &p->misc.p};
         uint64_t n_words = (m + 31) >> 5;
         if ((rc = launch(p, p->f_traj, (unsigned)((n_words + p->block - 1) / p->block), p->block, 0, args))) return rc;
-        CU_CHECK(cuMemcpyDtoHAsync(out + done * (n_steps + 1) * kw, p->misc.p, m * per_lane, p->stream));
+        // (after_chunk: the chunk's states [m][n_steps + 1][kw] are in p->misc, on the device)
+        if (after_chunk && (rc = after_chunk(done, m))) return rc;
+        if (out) CU_CHECK(cuMemcpyDtoHAsync(out + done * (n_steps + 1) * kw, p->misc.p, m * per_lane, p->stream));
         CU_CHECK(cuStreamSynchronize(p->stream));
         done += m;
     }
@@ -1227,6 +1268,36 @@ int bsi_attractor_states(bsi_plan *p, const uint64_t *key, uint64_t lambda, uint
     return run_trajectories(p, 0, nullptr, key, 1, lambda - 1, out, nullptr);
 }
 
+// Orbits the resolution kernels stored in the cycle dictionary, copied to the host: for each
+// stored attractor (key state = first state of its orbit) the offset and length of its orbit.
+static int read_dictionary(bsi_plan *p, std::vector<uint64_t> *orbit, std::map<std::vector<uint64_t>, std::pair<uint64_t, uint64_t>> *by_key) {
+    orbit->clear();
+    by_key->clear();
+    if (!p->dict.slots) return BSI_OK;
+    uint64_t cnt[2] = {0, 0};
+    CU_CHECK(cuMemcpyDtoHAsync(cnt, p->dict_ctr.p, 16, p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    const uint64_t n_attr = std::min<uint64_t>(cnt[1], p->dict.cap_attr);
+    if (n_attr == 0) return BSI_OK;
+    const uint64_t kw = (uint64_t)p->m.kw;
+    std::vector<uint32_t> dir(2 * n_attr);
+    CU_CHECK(cuMemcpyDtoHAsync(dir.data(), p->dict_dir.p, 8 * n_attr, p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    uint64_t hi = 0;
+    for (uint64_t a = 0; a < n_attr; ++a) hi = std::max<uint64_t>(hi, (uint64_t)dir[2 * a] + dir[2 * a + 1]);
+    hi = std::min<uint64_t>(hi, p->dict.cap_states);
+    orbit->resize(hi * kw);
+    CU_CHECK(cuMemcpyDtoHAsync(orbit->data(), p->dict_orbit.p, 8 * hi * kw, p->stream));
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    for (uint64_t a = 0; a < n_attr; ++a) {
+        const uint64_t base = dir[2 * a], lam = dir[2 * a + 1];
+        if (base + lam > hi) continue;
+        std::vector<uint64_t> key(orbit->begin() + base * kw, orbit->begin() + (base + 1) * kw);
+        (*by_key)[key] = {base, lam};
+    }
+    return BSI_OK;
+}
+
 int bsi_attractor_states_batch(bsi_plan *p, const uint64_t *keys, uint64_t n, uint64_t n_states,
                                uint64_t *out) {
     int rc = need_device(p, BSI_MODE_ATTRACT);
@@ -1234,7 +1305,107 @@ int bsi_attractor_states_batch(bsi_plan *p, const uint64_t *keys, uint64_t n, ui
     if (n == 0) return BSI_OK;
     if (!keys || !out || n_states == 0) return fail(BSI_E_ARG, "bad arguments");
     CtxGuard g(p);
-    return run_trajectories(p, 0, nullptr, keys, n, n_states - 1, out, nullptr);
+    // orbits the run already stored (cycle dictionary) are copied; only the others are regenerated
+    const uint64_t kw = (uint64_t)p->m.kw;
+    std::vector<uint64_t> orbit;
+    std::map<std::vector<uint64_t>, std::pair<uint64_t, uint64_t>> by_key;
+    if ((rc = read_dictionary(p, &orbit, &by_key))) return rc;
+    std::vector<uint64_t> rest_keys, rest_pos;
+    for (uint64_t i = 0; i < n; ++i) {
+        auto it = by_key.empty() ? by_key.end()
+                                 : by_key.find(std::vector<uint64_t>(keys + i * kw, keys + (i + 1) * kw));
+        if (it == by_key.end()) {
+            rest_pos.push_back(i);
+            rest_keys.insert(rest_keys.end(), keys + i * kw, keys + (i + 1) * kw);
+            continue;
+        }
+        const uint64_t base = it->second.first, lam = it->second.second;
+        for (uint64_t t = 0; t < n_states; ++t)
+            memcpy(out + (i * n_states + t) * kw, orbit.data() + (base + t % lam) * kw, 8 * kw);
+    }
+    if (rest_pos.empty()) return BSI_OK;
+    if (rest_pos.size() == n) return run_trajectories(p, 0, nullptr, keys, n, n_states - 1, out, nullptr);
+    std::vector<uint64_t> tmp(rest_pos.size() * n_states * kw);
+    if ((rc = run_trajectories(p, 0, nullptr, rest_keys.data(), rest_pos.size(), n_states - 1, tmp.data(), nullptr)))
+        return rc;
+    for (size_t r = 0; r < rest_pos.size(); ++r)
+        memcpy(out + rest_pos[r] * n_states * kw, tmp.data() + r * n_states * kw, 8 * n_states * kw);
+    return BSI_OK;
+}
+
+int bsi_attractor_activity(bsi_plan *p, const uint64_t *keys, const uint64_t *lams, uint64_t n,
+                           uint64_t *counts) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (n == 0) return BSI_OK;
+    if (!keys || !lams || !counts) return fail(BSI_E_ARG, "null pointer");
+    CtxGuard g(p);
+    const uint64_t kw = (uint64_t)p->m.kw, nn = (uint64_t)p->m.n;
+    std::vector<uint64_t> orbit;
+    std::map<std::vector<uint64_t>, std::pair<uint64_t, uint64_t>> by_key;
+    if ((rc = read_dictionary(p, &orbit, &by_key))) return rc;
+    // one launch over the orbits stored by the run; the others are regenerated and counted chunk by chunk
+    std::vector<uint64_t> start, lam, pos, rest_keys, rest_pos;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (lams[i] == 0) return fail(BSI_E_ARG, "attractor length 0");
+        auto it = by_key.empty() ? by_key.end()
+                                 : by_key.find(std::vector<uint64_t>(keys + i * kw, keys + (i + 1) * kw));
+        if (it != by_key.end() && it->second.second == lams[i]) {
+            start.push_back(it->second.first);
+            lam.push_back(lams[i]);
+            pos.push_back(i);
+        } else {
+            rest_pos.push_back(i);
+            rest_keys.insert(rest_keys.end(), keys + i * kw, keys + (i + 1) * kw);
+        }
+    }
+    auto count_on_device = [&](CUdeviceptr states, const std::vector<uint64_t> &st, const std::vector<uint64_t> &lm,
+                               const uint64_t *where) -> int {
+        const uint64_t m = st.size();
+        int r;
+        if ((r = ensure(p, p->misc4, 16 * m)) || (r = ensure(p, p->misc5, 8 * m * nn))) return r;
+        CU_CHECK(cuMemcpyHtoDAsync(p->misc4.p, st.data(), 8 * m, p->stream));
+        CU_CHECK(cuMemcpyHtoDAsync(p->misc4.p + 8 * m, lm.data(), 8 * m, p->stream));
+        CUdeviceptr d_start = p->misc4.p, d_lam = p->misc4.p + 8 * m;
+        void *args[] = {&states, &d_start, &d_lam, &p->misc5.p};
+        if ((r = launch(p, p->f_counts, (unsigned)m, 128, 0, args))) return r;
+        std::vector<uint64_t> host(m * nn);
+        CU_CHECK(cuMemcpyDtoHAsync(host.data(), p->misc5.p, 8 * m * nn, p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+        for (uint64_t j = 0; j < m; ++j) memcpy(counts + where[j] * nn, host.data() + j * nn, 8 * nn);
+        return BSI_OK;
+    };
+    if (!pos.empty() && (rc = count_on_device(p->dict_orbit.p, start, lam, pos.data()))) return rc;
+    if (rest_pos.empty()) return BSI_OK;
+    // regenerate the rest, one launch per power-of-two class of lengths (a long cycle must not inflate
+    // the buffers of many short ones)
+    std::map<int, std::vector<uint64_t>> classes;
+    for (uint64_t r = 0; r < rest_pos.size(); ++r) {
+        int cls = 0;
+        while ((1ull << cls) < lams[rest_pos[r]]) ++cls;
+        classes[cls].push_back(r);
+    }
+    for (auto &kv : classes) {
+        const std::vector<uint64_t> &members = kv.second;
+        uint64_t n_states = 0;
+        std::vector<uint64_t> ck;
+        for (uint64_t r : members) {
+            n_states = std::max(n_states, lams[rest_pos[r]]);
+            ck.insert(ck.end(), rest_keys.begin() + r * kw, rest_keys.begin() + (r + 1) * kw);
+        }
+        rc = run_trajectories(p, 0, nullptr, ck.data(), members.size(), n_states - 1, nullptr, nullptr,
+                              [&](uint64_t done, uint64_t m) -> int {
+                                  std::vector<uint64_t> st(m), lm(m), where(m);
+                                  for (uint64_t j = 0; j < m; ++j) {
+                                      st[j] = j * n_states;
+                                      lm[j] = lams[rest_pos[members[done + j]]];
+                                      where[j] = rest_pos[members[done + j]];
+                                  }
+                                  return count_on_device(p->misc.p, st, lm, where.data());
+                              });
+        if (rc) return rc;
+    }
+    return BSI_OK;
 }
 
 // ---- target ---------------------------------------------------------------------------------------
@@ -1328,6 +1499,359 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
     st.launches = p->launches - launches0;
     if (n_hits) *n_hits = written;
     if (stats) *stats = st;
+    return BSI_OK;
+}
+
+// ---- groups: one plan per device, one host process ------------------------------------------------
+// The one-process replacement of the reference's MPI task farm (mpi.py:193-340: master + workers, one
+// process per core): every device of the group takes a contiguous, word-aligned slice of the index
+// range (one host thread per device enqueues it), and the collection stage (mpi.py:296-332) is the
+// peers' export kernels writing their compacted tables straight into device 0's memory over NVLink
+// (peer access; a peer copy where that is not available), followed by ONE merge launch on device 0.
+}  // extern "C"
+
+struct bsi_group {
+    std::vector<bsi_plan *> plans;
+    std::vector<char> direct;           // device d writes into device 0's memory directly (peer access)
+    std::vector<DevBuf> staging;        // per device, on that device: payload when there is no peer access
+    std::vector<CUevent> done;          // per device: payload has reached device 0
+    DevBuf gather;                      // on device 0: headers [n - 1] + records [n - 1][cap]
+    uint64_t cap = 1024;                // records per payload
+    int mode = BSI_MODE_ATTRACT;
+};
+
+namespace {
+
+void shard(uint64_t b, uint64_t e, int d, int n, uint64_t *lo, uint64_t *hi) {
+    // contiguous slices of [b, e), cut at word boundaries (multiples of 32 problems)
+    const uint64_t w0 = b >> 5, w1 = (e + 31) >> 5, words = w1 - w0;
+    uint64_t a = (w0 + words * (uint64_t)d / (uint64_t)n) << 5, z = (w0 + words * (uint64_t)(d + 1) / (uint64_t)n) << 5;
+    *lo = std::min(std::max(a, b), e);
+    *hi = d == n - 1 ? e : std::min(std::max(z, b), e);
+}
+
+// runs fn(d) for every device of the group in its own host thread; first error wins
+template <typename F>
+int for_each_device(bsi_group *g, F fn) {
+    const int n = (int)g->plans.size();
+    std::vector<int> rcs(n, BSI_OK);
+    std::vector<std::string> errs(n);
+    auto body = [&](int d) {
+        rcs[d] = fn(d);
+        if (rcs[d] != BSI_OK) errs[d] = g_err;
+    };
+    if (n == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n; ++d) th.emplace_back(body, d);
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < n; ++d)
+        if (rcs[d] != BSI_OK) { g_err = "device " + std::to_string(g->plans[d]->device) + ": " + errs[d]; return rcs[d]; }
+    return BSI_OK;
+}
+
+int group_gather_buffers(bsi_group *g) {
+    const int n = (int)g->plans.size();
+    if (n < 2) return BSI_OK;
+    bsi_plan *p0 = g->plans[0];
+    const size_t rec = sizeof(bsi_attractor_rec);
+    int rc;
+    {
+        CtxGuard c0(p0);
+        if ((rc = ensure(p0, g->gather, (size_t)(n - 1) * (1 + g->cap) * rec))) return rc;
+    }
+    for (int d = 1; d < n; ++d) {
+        if (g->direct[d]) continue;
+        CtxGuard cd(g->plans[d]);
+        if ((rc = ensure(g->plans[d], g->staging[d], (1 + g->cap) * rec))) return rc;
+    }
+    return BSI_OK;
+}
+
+int regrow_table(bsi_plan *p, uint32_t log2) {
+    CtxGuard c(p);
+    CU_CHECK(cuStreamSynchronize(p->stream));
+    p->table_log2 = log2;
+    const size_t slot_bytes = (size_t)8 * p->m.kw + 32;
+    int rc = ensure(p, p->table, slot_bytes << p->table_log2);
+    if (rc) return rc;
+    CU_CHECK(cuMemsetD8Async(p->table.p, 0, p->table.bytes, p->stream));
+    return BSI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsi_group_create(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                     const bsi_target_desc *target, const bsi_plan_opts *opts, const int *devices,
+                     int n_devices, bsi_group **out) {
+    if (!out) return fail(BSI_E_ARG, "null output pointer");
+    *out = nullptr;
+    if (!cu().ok) return fail(BSI_E_CUDA, "%s", cu().why.c_str());
+    int count = 0;
+    CU_CHECK(cuDeviceGetCount(&count));
+    std::vector<int> devs;
+    if (n_devices <= 0) {
+        for (int d = 0; d < count; ++d) devs.push_back(d);
+    } else {
+        for (int d = 0; d < n_devices; ++d) devs.push_back(devices ? devices[d] : d);
+    }
+    if (devs.empty()) return fail(BSI_E_CUDA, "no CUDA device");
+    for (size_t a = 0; a < devs.size(); ++a)
+        for (size_t b = a + 1; b < devs.size(); ++b)
+            if (devs[a] == devs[b]) return fail(BSI_E_ARG, "device %d listed twice", devs[a]);
+    bsi_group *g = new bsi_group();
+    g->mode = mode;
+    const int n = (int)devs.size();
+    g->plans.assign(n, nullptr);
+    g->direct.assign(n, 0);
+    g->staging.resize(n);
+    g->done.assign(n, nullptr);
+    // the first plan specialises the kernels (NVRTC; cached per process), the others only load them
+    int rc = create_plan(network, space, mode, target, opts, devs[0], &g->plans[0]);
+    if (rc == BSI_OK && n > 1) {
+        std::vector<int> rcs(n, BSI_OK);
+        std::vector<std::string> errs(n);
+        std::vector<std::thread> th;
+        for (int d = 1; d < n; ++d)
+            th.emplace_back([&, d] {
+                rcs[d] = create_plan(network, space, mode, target, opts, devs[d], &g->plans[d]);
+                if (rcs[d] != BSI_OK) errs[d] = g_err;
+            });
+        for (auto &t : th) t.join();
+        for (int d = 1; d < n && rc == BSI_OK; ++d)
+            if (rcs[d] != BSI_OK) { rc = rcs[d]; g_err = errs[d]; }
+    }
+    if (rc == BSI_OK && n > 1 && mode == BSI_MODE_ATTRACT) {
+        bsi_plan *p0 = g->plans[0];
+        for (int d = 1; d < n; ++d) {
+            bsi_plan *pd = g->plans[d];
+            CtxGuard cd(pd);
+            int can = 0;
+            if (cu().p_cuDeviceCanAccessPeer(&can, pd->dev, p0->dev) == CUDA_SUCCESS && can) {
+                CUresult r = cu().p_cuCtxEnablePeerAccess(p0->ctx, 0);
+                g->direct[d] = (r == CUDA_SUCCESS || r == CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED) ? 1 : 0;
+            }
+            if (cu().p_cuEventCreate(&g->done[d], CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) {
+                rc = fail(BSI_E_CUDA, "cuEventCreate failed");
+                break;
+            }
+        }
+    }
+    if (rc != BSI_OK) {
+        std::string keep = g_err;
+        bsi_group_destroy(g);
+        g_err = keep;
+        return rc;
+    }
+    *out = g;
+    return BSI_OK;
+}
+
+void bsi_group_destroy(bsi_group *g) {
+    if (!g) return;
+    for (size_t d = 0; d < g->plans.size(); ++d) {
+        bsi_plan *p = g->plans[d];
+        if (!p) continue;
+        {
+            CtxGuard c(p);
+            if (p->stream) cu().p_cuStreamSynchronize(p->stream);
+            if (g->done[d]) cu().p_cuEventDestroy(g->done[d]);
+            give_back(p->device, g->staging[d]);
+            if (d == 0) give_back(p->device, g->gather);
+        }
+        bsi_plan_destroy(p);
+    }
+    delete g;
+}
+
+int bsi_group_size(const bsi_group *g, int *n_devices) {
+    if (!g || !n_devices) return fail(BSI_E_ARG, "null pointer");
+    *n_devices = (int)g->plans.size();
+    return BSI_OK;
+}
+
+int bsi_group_plan(bsi_group *g, int i, bsi_plan **plan) {
+    if (!g || !plan) return fail(BSI_E_ARG, "null pointer");
+    if (i < 0 || i >= (int)g->plans.size()) return fail(BSI_E_ARG, "no such member");
+    *plan = g->plans[i];
+    return BSI_OK;
+}
+
+int bsi_group_attract_run(bsi_group *g, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                          uint64_t max_attractor_l, bsi_run_stats *total, bsi_run_stats *per_device) {
+    if (!g) return fail(BSI_E_ARG, "null group");
+    if (g->mode != BSI_MODE_ATTRACT) return fail(BSI_E_ARG, "group was created for another mode");
+    const int n = (int)g->plans.size();
+    bsi_plan *p0 = g->plans[0];
+    if (idx_begin > idx_end || idx_end > p0->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    const size_t rec = sizeof(bsi_attractor_rec);
+    std::vector<bsi_run_stats> st(n);
+    for (int attempt = 0;; ++attempt) {
+        int rc = group_gather_buffers(g);
+        if (rc) return rc;
+        // every device: clear, run its slice, hand its table to device 0 -- all enqueued, no host wait
+        // (a run of several detection rounds reads queue lengths between rounds, in its own thread)
+        rc = for_each_device(g, [&](int d) -> int {
+            bsi_plan *p = g->plans[d];
+            uint64_t lo, hi;
+            shard(idx_begin, idx_end, d, n, &lo, &hi);
+            int r = bsi_attract_table_clear(p);
+            if (r) return r;
+            if ((r = attract_enqueue(p, lo, hi, max_t, max_attractor_l, nullptr, true))) return r;
+            if (d == 0) return BSI_OK;
+            CtxGuard c(p);
+            const CUdeviceptr hdr0 = g->gather.p + (size_t)(d - 1) * rec;
+            const CUdeviceptr recs0 = g->gather.p + (size_t)(n - 1) * rec + (size_t)(d - 1) * g->cap * rec;
+            if (g->direct[d]) {
+                if ((r = export_table(p, recs0, g->cap, nullptr, hdr0, false, false))) return r;
+            } else {
+                const CUdeviceptr mine = g->staging[d].p;
+                if ((r = export_table(p, mine + rec, g->cap, nullptr, mine, false, false))) return r;
+                CU_CHECK(cuMemcpyPeerAsync(hdr0, p0->ctx, mine, p->ctx, rec, p->stream));
+                CU_CHECK(cuMemcpyPeerAsync(recs0, p0->ctx, mine + rec, p->ctx, g->cap * rec, p->stream));
+            }
+            CU_CHECK(cuEventRecord(g->done[d], p->stream));
+            return BSI_OK;
+        });
+        bool failed = rc != BSI_OK;
+        std::string err = g_err;
+        if (!failed && n > 1) {
+            CtxGuard c0(p0);
+            for (int d = 1; d < n; ++d) CU_CHECK(cuStreamWaitEvent(p0->stream, g->done[d], 0));
+            CUdeviceptr hdrs = g->gather.p, recs = g->gather.p + (size_t)(n - 1) * rec;
+            uint32_t n_pay = (uint32_t)(n - 1);
+            void *args[] = {&p0->table.p, &p0->table_log2, &hdrs, &recs, &n_pay, &g->cap, &p0->ctr.p};
+            if ((rc = launch(p0, p0->f_merge_payloads, (unsigned)std::min<uint64_t>(p0->n_sms, 8 * n_pay), 256, 0, args))) {
+                failed = true;
+                err = g_err;
+            }
+        }
+        // collect every device's run (also those that were enqueued before another one failed)
+        bool overflow = false;
+        for (int d = 0; d < n; ++d) {
+            bsi_plan *p = g->plans[d];
+            if (!p->pending) continue;
+            CtxGuard c(p);
+            int r = attract_collect(p, &st[d]);
+            if (r == BSI_E_CAPACITY) overflow = true;
+            else if (r != BSI_OK && !failed) { failed = true; rc = r; err = g_err; }
+        }
+        if (failed) { g_err = err; return rc; }
+        uint64_t need = 0;
+        if (n > 1 && !overflow) {
+            // did every payload fit, and did the merged table hold?
+            CtxGuard c0(p0);
+            std::vector<bsi_attractor_rec> hdr(n - 1);
+            uint64_t full = 0;
+            CU_CHECK(cuMemcpyDtoHAsync(hdr.data(), g->gather.p, (size_t)(n - 1) * rec, p0->stream));
+            CU_CHECK(cuMemcpyDtoHAsync(&full, p0->ctr.p + offsetof(Counters, table_full), 8, p0->stream));
+            CU_CHECK(cuStreamSynchronize(p0->stream));
+            for (auto &h : hdr) need = std::max<uint64_t>(need, h.key[0]);
+            if (full) overflow = true;
+        }
+        if (overflow) {
+            // more attractors than the table holds: the reference's store simply grows (attract.py:405-455),
+            // so grow the tables of all members and run the job again
+            uint32_t log2 = 0;
+            for (bsi_plan *p : g->plans) log2 = std::max(log2, p->table_log2);
+            if (log2 >= 28 || attempt >= 6) return fail(BSI_E_CAPACITY, "attractor table overflow at 2^%u slots", log2);
+            log2 = std::min<uint32_t>(28, log2 + 2);
+            for (bsi_plan *p : g->plans) if ((rc = regrow_table(p, log2))) return rc;
+            continue;
+        }
+        if (need > g->cap) {                 // a payload was larger than the gather buffer: run again with room
+            while (g->cap < need) g->cap *= 2;
+            if (attempt >= 6) return fail(BSI_E_CAPACITY, "table exchange did not converge");
+            continue;
+        }
+        break;
+    }
+    if (per_device) for (int d = 0; d < n; ++d) per_device[d] = st[d];
+    if (total) {
+        bsi_run_stats t{};
+        for (int d = 0; d < n; ++d) {
+            t.n_problems += st[d].n_problems; t.n_found += st[d].n_found; t.n_without += st[d].n_without;
+            t.steps += st[d].steps; t.device_steps += st[d].device_steps; t.launches += st[d].launches;
+            t.rounds = std::max(t.rounds, st[d].rounds);
+            t.ms_total = std::max(t.ms_total, st[d].ms_total);
+            t.ms_main = std::max(t.ms_main, st[d].ms_main);
+            t.ms_resolve = std::max(t.ms_resolve, st[d].ms_resolve);
+        }
+        t.launches += n > 1 ? (uint64_t)n : 0;        // the peers' exports + the merge
+        *total = t;
+    }
+    return BSI_OK;
+}
+
+int bsi_group_target_run(bsi_group *g, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                         uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,
+                         bsi_run_stats *total) {
+    if (!g) return fail(BSI_E_ARG, "null group");
+    if (g->mode != BSI_MODE_TARGET) return fail(BSI_E_ARG, "group was created for another mode");
+    const int n = (int)g->plans.size();
+    if (idx_begin > idx_end || idx_end > g->plans[0]->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    if (cap && (!hit_index || !hit_t)) return fail(BSI_E_ARG, "null hit buffers");
+    // slices are ascending and each device reports its hits in index order, so concatenation in device
+    // order IS the enumeration order the reference reports in (simulate.py:149-178); the first `cap`
+    // overall are among the first `cap` of each slice
+    std::vector<std::vector<uint64_t>> hi(n), ht(n);
+    std::vector<uint64_t> got(n, 0);
+    std::vector<bsi_run_stats> st(n);
+    int rc = for_each_device(g, [&](int d) -> int {
+        uint64_t lo, up;
+        shard(idx_begin, idx_end, d, n, &lo, &up);
+        const uint64_t c = std::min<uint64_t>(cap, up - lo);
+        hi[d].resize(c + 1);
+        ht[d].resize(c + 1);
+        return bsi_target_run(g->plans[d], lo, up, max_t, hi[d].data(), ht[d].data(), c, &got[d], &st[d]);
+    });
+    if (rc) return rc;
+    uint64_t written = 0;
+    bsi_run_stats t{};
+    for (int d = 0; d < n; ++d) {
+        for (uint64_t i = 0; i < got[d] && written < cap; ++i, ++written) {
+            hit_index[written] = hi[d][i];
+            hit_t[written] = ht[d][i];
+        }
+        t.n_problems += st[d].n_problems; t.n_found += st[d].n_found; t.n_without += st[d].n_without;
+        t.steps += st[d].steps; t.device_steps += st[d].device_steps; t.launches += st[d].launches;
+        t.rounds = std::max(t.rounds, st[d].rounds);
+        t.ms_total = std::max(t.ms_total, st[d].ms_total);
+        t.ms_main = std::max(t.ms_main, st[d].ms_main);
+    }
+    if (n_hits) *n_hits = written;
+    if (total) *total = t;
+    return BSI_OK;
+}
+
+int bsi_group_simulate_run(bsi_group *g, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                           uint64_t *states_out, bsi_run_stats *total) {
+    if (!g) return fail(BSI_E_ARG, "null group");
+    const int n = (int)g->plans.size();
+    if (idx_begin > idx_end || idx_end > g->plans[0]->m.n_problems) return fail(BSI_E_ARG, "bad index range");
+    std::vector<bsi_run_stats> st(n);
+    const uint64_t per_problem = (max_t + 1) * (uint64_t)g->plans[0]->m.kw;
+    int rc = for_each_device(g, [&](int d) -> int {
+        uint64_t lo, up;
+        shard(idx_begin, idx_end, d, n, &lo, &up);
+        if (lo == up) return BSI_OK;
+        return bsi_simulate_run(g->plans[d], lo, up, max_t, states_out + (lo - idx_begin) * per_problem, &st[d]);
+    });
+    if (rc) return rc;
+    if (total) {
+        bsi_run_stats t{};
+        for (int d = 0; d < n; ++d) {
+            t.n_problems += st[d].n_problems; t.n_found += st[d].n_found; t.steps += st[d].steps;
+            t.device_steps += st[d].device_steps; t.launches += st[d].launches;
+            t.ms_total = std::max(t.ms_total, st[d].ms_total);
+            t.ms_main = std::max(t.ms_main, st[d].ms_main);
+        }
+        *total = t;
+    }
     return BSI_OK;
 }
 

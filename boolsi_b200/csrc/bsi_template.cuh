@@ -48,6 +48,9 @@ __device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
 }
 
 #define BSI_MAX_CK 72
+#ifndef BSI_DICT_MIN_LAM
+#define BSI_DICT_MIN_LAM 8u          // cycles up to this length are walked, longer ones looked up
+#endif
 
 // 32x32 bit-matrix transpose in place (Hacker's Delight 7-3): B[r] bit c = A[31-c] bit 31-r.
 // Turns 32 node words (bit = lane) into 32 lane words (bit = node) and back in 5 x 16 butterfly
@@ -221,6 +224,168 @@ __device__ __noinline__ void bsi_table_add(BsiSlot *table, u32 log2_slots, const
         }
     }
     atomicExch(&ctr->table_full, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cycle dictionary: on-cycle state -> (attractor, phase)
+// ---------------------------------------------------------------------------------------------
+// The number of DIFFERENT attractors of a network is tiny next to the number of trajectories that
+// fall into them (reference attract.py:374-402 aggregates millions of problems into a handful of
+// records), so the canonical key of an attractor -- the minimum state code over the cycle,
+// model.py:140-149 / attract.py:296 -- is worked out by a walk ONCE per attractor and then looked
+// up: the first thread that resolves a lane of a new attractor stores the whole orbit, key state
+// first, in `orbit` and enters every state into an open-addressing table.  A later lane that
+// matched state y finds (base, phase) with one probe; its key is orbit[base] and the periodic
+// extension of its cycle at any time is orbit[base + (phase - dt) mod lambda] -- no key walk and no
+// per-lane advance walk.  The dictionary is a CACHE of facts about the network's dynamics: a
+// miss, a full table, or a racing writer only mean that the lane takes the walks; results never
+// depend on it.  Slots go 0 (empty) -> 1 (being written, a few instructions) -> 2 (ready), 3
+// (tombstone: orbit storage exhausted) or 4 (the key state of an attractor whose orbit is still
+// being stored: reserved, not yet usable); a slot's fields are written once.  NO state of an
+// attractor is published before its whole orbit is in memory: a reader that finds a state may
+// read any phase of the orbit.
+struct __align__(16) BsiDictSlot {
+    u32 flag, idx, base, lam;       // idx = base + phase
+    u64 st[BSI_KW];
+};
+struct BsiDict {
+    BsiDictSlot *slots;             // nullptr: dictionary off
+    u64 *orbit;                     // [cap_states][KW]
+    u64 *n_states;                  // fill counter of `orbit` (may run past cap_states)
+    u64 *n_attr;                    // number of stored attractors
+    u32 *dir;                       // [cap_attr][2]: (base, lambda) of every stored attractor
+    u32 log2_slots, cap_states, cap_attr, pad;
+};
+
+__device__ __forceinline__ void bsi_dict_head(const BsiDictSlot *s, u32 &f, u32 &idx, u32 &base, u32 &lam) {
+#ifdef BSI_HOST_EMUL
+    f = __atomic_load_n(&s->flag, __ATOMIC_SEQ_CST);
+    idx = s->idx; base = s->base; lam = s->lam;
+#else
+    // one 16-byte transaction: the four fields are seen together
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(f), "=r"(idx), "=r"(base), "=r"(lam) : "l"(s));
+#endif
+}
+__device__ __forceinline__ u64 bsi_ld_u64(const u64 *p) { return *((const volatile u64 *)p); }
+// The same through the L2 only (ld.global.cg), NOT volatile: independent loads of a batch may be
+// issued back to back, so that a word's 32 lookups cost a few L2 round trips and not 32.
+__device__ __forceinline__ void bsi_dict_head_cg(const BsiDictSlot *s, u32 &f, u32 &idx, u32 &base, u32 &lam) {
+#ifdef BSI_HOST_EMUL
+    bsi_dict_head(s, f, idx, base, lam);
+#else
+    asm("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f), "=r"(idx), "=r"(base), "=r"(lam) : "l"(s));
+#endif
+}
+__device__ __forceinline__ u64 bsi_ldcg_u64(const u64 *p) {
+#ifdef BSI_HOST_EMUL
+    return *((const volatile u64 *)p);
+#else
+    u64 v;
+    asm("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#endif
+}
+
+// state -> (idx, base, lambda); false on a miss (or on a slot that is still being written)
+__device__ __forceinline__ bool bsi_dict_find(const BsiDict &d, const u64 *st, u32 &idx, u32 &base, u32 &lam) {
+    const u32 mask = (1u << d.log2_slots) - 1u;
+    u32 pos = (u32)bsi_hash_key(st) & mask;
+#pragma unroll 1
+    for (u32 probe = 0; probe < 32u; ++probe, pos = (pos + 1u) & mask) {
+        const BsiDictSlot *s = d.slots + pos;
+        u32 f;
+        bsi_dict_head(s, f, idx, base, lam);
+        if (f == 2u || f == 4u) {
+            // (a state word that lags behind the flag reads as zero or as itself: at worst a miss)
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) same = same && (bsi_ld_u64(&s->st[i]) == st[i]);
+            if (same) return f == 2u;
+        } else if (f != 3u) {
+            return false;
+        }
+    }
+    return false;
+}
+
+// enter state `st` = orbit[idx] of the attractor stored at `base` (the caller has written the orbit entry)
+__device__ __noinline__ void bsi_dict_put(const BsiDict &d, const u64 *st, u32 idx, u32 base, u32 lam) {
+    const u32 mask = (1u << d.log2_slots) - 1u;
+    u32 pos = (u32)bsi_hash_key(st) & mask;
+    for (u32 probe = 0; probe < 32u; ++probe, pos = (pos + 1u) & mask) {
+        BsiDictSlot *s = d.slots + pos;
+        u32 f = *((volatile u32 *)&s->flag);
+        if (f == 0u) {
+            const u32 old = atomicCAS(&s->flag, 0u, 1u);
+            if (old == 0u) {
+                s->idx = idx; s->base = base; s->lam = lam;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) s->st[i] = st[i];
+                __threadfence();
+                atomicExch(&s->flag, 2u);
+                return;
+            }
+            f = old;
+        }
+        while (f == 1u) f = *((volatile u32 *)&s->flag);      // (a writer never waits inside this section)
+        if (f == 2u || f == 4u) {
+            __threadfence();
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) same = same && (bsi_ld_u64(&s->st[i]) == st[i]);
+            if (same) return;
+        }
+    }
+}
+
+// Claim the attractor with key state `key` and length `lam`: true if THIS thread reserved the key
+// (slot state 4; it then owns orbit[base .. base + lam), must store the orbit, enter the other states
+// and finally publish the key with bsi_dict_publish), false if the key is already there or reserved,
+// the table is crowded, or the orbit storage is exhausted.
+__device__ __noinline__ bool bsi_dict_claim(const BsiDict &d, const u64 *key, u32 lam, u32 &base, u32 &slot) {
+    if (bsi_ld_u64(d.n_states) + lam > (u64)d.cap_states || bsi_ld_u64(d.n_attr) >= (u64)d.cap_attr) return false;
+    const u32 mask = (1u << d.log2_slots) - 1u;
+    u32 pos = (u32)bsi_hash_key(key) & mask;
+    for (u32 probe = 0; probe < 32u; ++probe, pos = (pos + 1u) & mask) {
+        BsiDictSlot *s = d.slots + pos;
+        u32 f = *((volatile u32 *)&s->flag);
+        if (f == 0u) {
+            const u32 old = atomicCAS(&s->flag, 0u, 1u);
+            if (old == 0u) {
+                const u64 b = atomicAdd(d.n_states, (u64)lam);
+                const u64 a = b + lam <= (u64)d.cap_states ? atomicAdd(d.n_attr, 1ull) : (u64)d.cap_attr;
+                if (a >= (u64)d.cap_attr) {
+                    atomicExch(&s->flag, 3u);
+                    return false;
+                }
+                base = (u32)b;
+                slot = pos;
+                d.dir[2 * a] = base;
+                d.dir[2 * a + 1] = lam;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) { d.orbit[b * BSI_KW + i] = key[i]; s->st[i] = key[i]; }
+                s->idx = base; s->base = base; s->lam = lam;
+                __threadfence();
+                atomicExch(&s->flag, 4u);
+                return true;
+            }
+            f = old;
+        }
+        while (f == 1u) f = *((volatile u32 *)&s->flag);
+        if (f == 2u || f == 4u) {
+            __threadfence();
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) same = same && (bsi_ld_u64(&s->st[i]) == key[i]);
+            if (same) return false;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ void bsi_dict_publish(const BsiDict &d, u32 slot) {
+    __threadfence();
+    atomicExch(&d.slots[slot].flag, 2u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -770,27 +935,94 @@ __device__ __forceinline__ void bsi_key_core(u64 (*cw_)[BSI_KW], u32 valid, u32 
     }
 }
 
-__device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64 w) {
-    u32 valid = 0u, lam_max = 0u;
+// Store the orbit of `key` (length lam >= 2, reserved at `base` / `slot` by bsi_dict_claim), enter
+// its states into the dictionary and publish it.  The thread's 32 lanes walk 32 different phases of
+// the SAME orbit: a first pass brings lane j to phase j * s (s = ceil(lam / 32); lanes drop out of the
+// advancing set one by one), a second pass of s steps then yields 32 states per step, so the 32x32
+// transposes that turn bit-sliced words into state codes are paid s times and not lam times.  Only
+// when the whole orbit is in memory are its states entered (read back from there), the key last.
+__device__ __noinline__ void bsi_dict_learn(const BsiDict &d, const u64 *key, u32 lam, u32 base, u32 slot) {
+    BSI_FOR_NODES(BSI_DECL_A)
+    BSI_FOR_NODES(BSI_DECL_B)
+#define BSI_BCAST_NODE(i) a##i = 0u - (u32)((key[(i) >> 6] >> ((i) & 63)) & 1ull);
+    BSI_FOR_NODES(BSI_BCAST_NODE)
+#undef BSI_BCAST_NODE
+    const u32 s = (lam + 31u) / 32u;
+#define BSI_HOLD_AB(i) a##i = bsi_lop3<0xCA>(go_, b##i, a##i);
+    for (u32 k = 0; k < 31u * s; ++k) {
+        const u32 go_ = ~((2u << (k / s)) - 1u);          // lanes j with j * s > k
+        BSI_UPDATE(b, a)
+        BSI_FOR_NODES(BSI_HOLD_AB)
+    }
+#undef BSI_HOLD_AB
     u64 cw_[32][BSI_KW];
+    for (u32 q = 0; q < s; ++q) {
+        BSI_UNPACK(cw_, a)
+#pragma unroll 1
+        for (u32 j = 0; j < 32u; ++j) {
+            const u32 ph = j * s + q;
+            if (ph >= 1u && ph < lam) {
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) d.orbit[(u64)(base + ph) * BSI_KW + i] = cw_[j][i];
+            }
+        }
+        BSI_UPDATE(b, a)
+        BSI_FOR_NODES(BSI_COPY_AB)
+    }
+    __threadfence();
+#pragma unroll 1
+    for (u32 ph = 1; ph < lam; ++ph) {
+        u64 st[BSI_KW];
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) st[i] = bsi_ld_u64(&d.orbit[(u64)(base + ph) * BSI_KW + i]);
+        bsi_dict_put(d, st, base + ph, base, lam);
+    }
+    bsi_dict_publish(d, slot);
+}
+
+__device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64 w, const BsiDict &dict) {
+    u32 valid = 0u, lam_max = 0u, miss = 0u;
+    u64 cw_[32][BSI_KW];
+    u32 lam_[32];
 #pragma unroll 1
     for (u32 l = 0; l < 32; ++l) {
         const u64 q = BSI_Q(w, l);
         const bool in = q < n_found;
 #pragma unroll
         for (int i = 0; i < BSI_KW; ++i) cw_[l][i] = in ? found_q[q].y[i] : 0ull;
+        lam_[l] = in ? found_q[q].lam : 0u;
         if (in) {
             valid |= 1u << l;
-            lam_max = max(lam_max, found_q[q].lam);
+            lam_max = max(lam_max, lam_[l]);
         }
     }
     if (lam_max <= 1u) return;
+    // lanes whose cycle is already in the dictionary take their key from there
+    if (dict.slots) {
+#pragma unroll 4
+        for (u32 l = 0; l < 32; ++l) {
+            if (lam_[l] <= 1u) continue;
+            u32 idx, base, lamd;
+            if (bsi_dict_find(dict, cw_[l], idx, base, lamd) && lamd == lam_[l]) {
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) found_q[BSI_Q(w, l)].key[i] = bsi_ld_u64(&dict.orbit[(u64)base * BSI_KW + i]);
+            } else {
+                miss |= 1u << l;
+            }
+        }
+        if (!miss) return;
+    } else {
+        miss = valid;
+    }
     bsi_key_core(cw_, valid, lam_max);
 #pragma unroll 1
     for (u32 l = 0; l < 32; ++l) {
-        if ((valid >> l) & 1u) {
+        if ((miss >> l) & 1u) {
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) found_q[BSI_Q(w, l)].key[i] = cw_[l][i];
+            // (no learning here: this is the latency-oriented path, where every word of the queue is in
+            //  flight at once -- nobody would profit before the kernel ends, and the walk of a long
+            //  orbit would sit on the critical path of the step)
         }
     }
 }
@@ -811,10 +1043,13 @@ struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it
 
 // EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in its y field, all
 // starting from the dense problem-index word in its word field, c0 = 0); otherwise word w of found_q.
+// `keep` always receives lambda and c0 of the lanes; with KEEP also their canonical keys (from the
+// cycle dictionary when it knows every cycle of the word, else by the walk of bsi_key_core -- the
+// walked cycles are then entered into the dictionary).
 template <bool WRITE_PAD, bool KEEP, bool EARLY>
 __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
                                             BsiCounters *ctr, BsiKeep *keep, const BsiEarlyQ &eq,
-                                            u32 &valid_out) {
+                                            const BsiDict &dict, bool learn, u32 &valid_out) {
     const u32 tid = threadIdx.x;
     {
         BSI_FOR_NODES(BSI_DECL_A)
@@ -836,6 +1071,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             for (u32 l = 0; l < 32; ++l) lc_[l] = ((valid >> l) & 1u) ? ent.lamc[l * 32u] : 1ull;
 #pragma unroll 1
             for (u32 l = 0; l < 32; ++l) {
+                keep->lam[l] = 0u;
                 if (!((valid >> l) & 1u)) continue;
                 const u64 lc = lc_[l];
                 const u32 lam = (u32)lc, c = (u32)(lc >> 32);
@@ -855,10 +1091,11 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             u64 x_[BSI_KW];
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) { cw_[l][i] = 0ull; cz_[l][i] = 0ull; x_[i] = 0ull; }
+            keep->lam[l] = 0u;
             if (q < n_found) {
                 const BsiFound r = found_q[q];
                 valid |= 1u << l;
-                const u32 adv = (r.lam - (r.c - r.c0) % r.lam) % r.lam;
+                const u32 adv = r.lam == 1u ? 0u : (r.lam - (r.c - r.c0) % r.lam) % r.lam;
                 aux_s[l * BSI_BLOCK + tid] = adv;
                 adv_max = max(adv_max, adv);
                 c_max = max(c_max, r.c - r.c0);      // the walk is at most c - c0 steps long
@@ -873,10 +1110,10 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #pragma unroll
                     for (int i = 0; i < BSI_KW; ++i) cz_[l][i] = r.z[i];
                 }
+                keep->lam[l] = r.lam;
+                keep->c0[l] = r.c0;
+                lam_max = max(lam_max, r.lam);
                 if (KEEP) {
-                    keep->lam[l] = r.lam;
-                    keep->c0[l] = r.c0;
-                    lam_max = max(lam_max, r.lam);
 #pragma unroll
                     for (int i = 0; i < BSI_KW; ++i) keep->key[l][i] = r.y[i];
                 }
@@ -885,7 +1122,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
         bool uniform = false;
-        if (KEEP && !EARLY) keep->uniform = 0u;
+        if (!EARLY) keep->uniform = 0u;
         if (EARLY) {
             BSI_LOAD_MEM(b, ent.y, 32)
             if (lam_max <= 1u && valid) {
@@ -913,35 +1150,112 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             if (!uniform) BSI_UNPACK(keep->key, b)   // the states as codes: keys of the fixed points
             keep->uniform = uniform ? 1u : 0u;
         }
-        // (throughput paths) the canonical keys, computed here: no separate pass over the records
-        if (KEEP) bsi_key_core(keep->key, valid, lam_max);
-        (void)lam_max;
-        valid_out = valid;
-        if (EARLY) {
-            if (!uniform) BSI_LOAD_MEM(b, ent.y, 32)      // (again: the transposes took the registers)
-        } else {
-            BSI_PACK(b, cw_)
-        }
-        // ---- b <- P(c0): advance each lane by its own number of steps -------------------------
-#define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
-        {
-            u32 go_ = 0u, next_ev = 0u;
-            for (u32 k = 0; k < adv_max; ++k) {
-                if (k == next_ev) {
-                    go_ = 0u;
-                    next_ev = 0xFFFFFFFFu;
+        // ---- lanes on cycles (lambda > 1): does the dictionary know every one of them? -----------
+        u64 (*const ycw_)[BSI_KW] = EARLY ? keep->key : cw_;      // the matched states as codes
+        u32 dbase_[32], dphase_[32];
+        u32 miss = 0u;
+        bool use_dict = false;
+        if (lam_max > 1u) {
+            // (short cycles are walked: the key walk and the advance of a word take lam_max - 1 steps
+            //  each, which is cheaper than 32 lookups and two 32x32 transposes up to about 8 states)
+            if (dict.slots && lam_max > BSI_DICT_MIN_LAM) {
+                const u32 mask_ = (1u << dict.log2_slots) - 1u;
 #pragma unroll 1
-                    for (u32 l = 0; l < 32; ++l) {
-                        if (!((valid >> l) & 1u)) continue;
-                        u32 adv = aux_s[l * BSI_BLOCK + tid];
-                        if (adv > k) { go_ |= 1u << l; next_ev = min(next_ev, adv); }
+                for (u32 l0 = 0; l0 < 32; l0 += 8) {
+                    // eight independent probes in flight, then the compares
+                    u32 f_[8], idx_[8], base_[8], lamd_[8];
+                    u64 st_[8][BSI_KW];
+#pragma unroll
+                    for (u32 k = 0; k < 8; ++k) {
+                        const BsiDictSlot *s_ = dict.slots + ((u32)bsi_hash_key(ycw_[l0 + k]) & mask_);
+                        bsi_dict_head_cg(s_, f_[k], idx_[k], base_[k], lamd_[k]);
+#pragma unroll
+                        for (int i = 0; i < BSI_KW; ++i) st_[k][i] = bsi_ldcg_u64(&s_->st[i]);
+                    }
+#pragma unroll
+                    for (u32 k = 0; k < 8; ++k) {
+                        const u32 l = l0 + k;
+                        if (keep->lam[l] <= 1u) continue;
+                        bool hit = f_[k] == 2u;
+#pragma unroll
+                        for (int i = 0; i < BSI_KW; ++i) hit = hit && st_[k][i] == ycw_[l][i];
+                        // (not in its first slot: the full probe sequence)
+                        if (!hit) hit = bsi_dict_find(dict, ycw_[l], idx_[k], base_[k], lamd_[k]);
+                        if (hit && lamd_[k] == keep->lam[l]) {
+                            dbase_[l] = base_[k];
+                            dphase_[l] = idx_[k] - base_[k];
+                        } else {
+                            miss |= 1u << l;
+                        }
                     }
                 }
-                BSI_UPDATE(c, b)
-                BSI_FOR_NODES(BSI_HOLD_NODE)
+                use_dict = miss == 0u;
             }
         }
+        valid_out = valid;
+        if (lam_max > 1u) { if (use_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) } }
+        if (use_dict) {
+            // keys and P(c0) straight from the stored orbits: P(c0) = y advanced by adv steps
+            u64 cp_[32][BSI_KW];
+#pragma unroll 8
+            for (u32 l = 0; l < 32; ++l) {
+                const u32 lam = keep->lam[l];
+                if (lam > 1u) {
+                    u32 ph = dphase_[l] + aux_s[l * BSI_BLOCK + tid];
+                    if (ph >= lam) ph -= lam;
+                    const u64 *po = dict.orbit + (u64)(dbase_[l] + ph) * BSI_KW;
+                    const u64 *pk = dict.orbit + (u64)dbase_[l] * BSI_KW;
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) {
+                        cp_[l][i] = bsi_ldcg_u64(po + i);
+                        if (KEEP) keep->key[l][i] = bsi_ldcg_u64(pk + i);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BSI_KW; ++i) cp_[l][i] = lam ? ycw_[l][i] : 0ull;
+                }
+            }
+            BSI_PACK(b, cp_)
+        } else {
+            // (throughput paths) the canonical keys, computed here: no separate pass over the records
+            if (KEEP) {
+                bsi_key_core(keep->key, valid, lam_max);
+                if (dict.slots && miss && learn) {
+                    // the walked cycles go into the dictionary (once per attractor: the claim decides)
+#pragma unroll 1
+                    for (u32 l = 0; l < 32; ++l) {
+                        u32 base, slot;
+                        if (((miss >> l) & 1u) && bsi_dict_claim(dict, keep->key[l], keep->lam[l], base, slot))
+                            bsi_dict_learn(dict, keep->key[l], keep->lam[l], base, slot);
+                    }
+                }
+            }
+            if (EARLY) {
+                if (!uniform) BSI_LOAD_MEM(b, ent.y, 32)      // (again: the transposes took the registers)
+            } else {
+                BSI_PACK(b, cw_)
+            }
+            // ---- b <- P(c0): advance each lane by its own number of steps ---------------------
+#define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
+            {
+                u32 go_ = 0u, next_ev = 0u;
+                for (u32 k = 0; k < adv_max; ++k) {
+                    if (k == next_ev) {
+                        go_ = 0u;
+                        next_ev = 0xFFFFFFFFu;
+#pragma unroll 1
+                        for (u32 l = 0; l < 32; ++l) {
+                            if (!((valid >> l) & 1u)) continue;
+                            u32 adv = aux_s[l * BSI_BLOCK + tid];
+                            if (adv > k) { go_ |= 1u << l; next_ev = min(next_ev, adv); }
+                        }
+                    }
+                    BSI_UPDATE(c, b)
+                    BSI_FOR_NODES(BSI_HOLD_NODE)
+                }
+            }
 #undef BSI_HOLD_NODE
+        }
         // ---- a <- x_c0: from the problem index (c0 = 0) or the shipped checkpoint state -----------
         {
             // the prefix macro works on (a, b): park P(c0) in c meanwhile
@@ -974,7 +1288,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         }
         // ---- lock-step: mu = first j with x_j == P(j) -------------------------------------------
         u32 alive = valid;
-#define BSI_LOCK(A, B, Tn, J)                                                     \
+#define BSI_LOCK_CMP(A, B, J)                                                     \
     {                                                                             \
         u32 p_ = ~alive, q_ = 0u;                                                 \
         BSI_CMP_FILTER(p_, q_, A, B)                                              \
@@ -989,9 +1303,25 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
                 aux_s[l_ * BSI_BLOCK + tid] = (J);                                \
             }                                                                     \
         }                                                                         \
+    }
+#define BSI_LOCK(A, B, Tn, J)                                                     \
+    {                                                                             \
+        BSI_LOCK_CMP(A, B, J)                                                     \
         if (alive) { BSI_UPDATE(Tn, A) BSI_UPDATE(A, B) }                         \
     }
-        {
+        if (lam_max <= 1u) {
+            // every lane ends in a fixed point: P is constant (= b), only x moves (a <-> c)
+            u32 j = 0;
+            while (alive && j <= c_max) {
+                BSI_LOCK_CMP(a, b, j)
+                if (!alive || j + 1 > c_max) break;
+                BSI_UPDATE(c, a)
+                BSI_LOCK_CMP(c, b, j + 1)
+                if (!alive || j + 2 > c_max) break;
+                BSI_UPDATE(a, c)
+                j += 2;
+            }
+        } else {
             u32 j = 0;
             while (alive && j <= c_max) {
                 BSI_LOCK(a, b, c, j)
@@ -1003,6 +1333,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             }
         }
 #undef BSI_LOCK
+#undef BSI_LOCK_CMP
         if (alive) atomicExch(&ctr->internal_error, 1ull);
         // mu - c0 stays in aux_s; for bsi_resolve_finish (another kernel) mu goes into the record
         if (WRITE_PAD) {
@@ -1146,7 +1477,7 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 #if BSI_UNIT != 5 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u64 max_attractor_l,
-               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr, const BsiDict dict) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
     if (bsi_latency_mode(n_found, ctr, few_words)) return;
@@ -1159,7 +1490,7 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
         u32 lanes = 0u;                  // threads without a word stay for the warp-level aggregation
         if (w < n_words && BSI_Q(w, 0) < n_found)
-            bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, lanes);
+            bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, dict, true, lanes);
         __syncwarp();
         bsi_finish_word<true, true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
                                     ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
@@ -1176,7 +1507,7 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u64 *n_found_p,
                   u64 few_words, u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
-                  u32 log2_slots, BsiCounters *ctr) {
+                  u32 log2_slots, BsiCounters *ctr, const BsiDict dict) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_early = *n_early_p;
     if (n_early == 0) return;
@@ -1188,7 +1519,7 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u
         const u64 e = bsi_grab_word(&ctr->next_word4);
         if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
         u32 lanes = 0u;
-        if (e < n_early) bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, lanes);
+        if (e < n_early) bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, dict, true, lanes);
         __syncwarp();
         bsi_finish_word<true, true>(nullptr, 0, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
                                     steps, n_acc, n_rej, aux_s, &keep, lanes);
@@ -1202,7 +1533,7 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_base, u64 early_cap,
             u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,
-            BsiCounters *ctr) {
+            BsiCounters *ctr, const BsiDict dict) {
     __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_found = *n_found_p;
     if (!bsi_latency_mode(n_found, ctr, few_words)) return;
@@ -1219,15 +1550,17 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
         if (t < w32) {
             if (BSI_Q(t, 0) < n_found) {
                 u32 lanes = 0u;
-                bsi_mu_word<true, false, false>(found_q, n_found, t, aux_s, ctr, nullptr,
-                                                bsi_early_view(nullptr, 0), lanes);
+                BsiKeep keep;
+                bsi_mu_word<true, false, false>(found_q, n_found, t, aux_s, ctr, &keep,
+                                                bsi_early_view(nullptr, 0), dict, false, lanes);
             }
         } else if (t < 2 * w32) {
-            if (BSI_Q(t - w32, 0) < n_found) bsi_key_word(found_q, n_found, t - w32);
+            if (BSI_Q(t - w32, 0) < n_found) bsi_key_word(found_q, n_found, t - w32, dict);
         } else if (t - 2 * w32 < n_early) {
             BsiKeep keep;
             u32 lanes = 0u;
-            bsi_mu_word<false, true, true>(nullptr, 0, t - 2 * w32, aux_s, ctr, &keep, eq, lanes);
+            // (no learning on the latency-oriented path: see bsi_key_word)
+            bsi_mu_word<false, true, true>(nullptr, 0, t - 2 * w32, aux_s, ctr, &keep, eq, dict, false, lanes);
             bsi_finish_word<true, false>(nullptr, 0, t - 2 * w32, T, max_attractor_l, stop_t_cap, table,
                                   log2_slots, ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
         }
@@ -1312,6 +1645,27 @@ extern "C" __global__ void bsi_table_merge(BsiSlot *table, u32 log2_slots, const
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) key[k] = recs[i].key[k];
         bsi_table_add(table, log2_slots, key, recs[i].n, recs[i].s1, recs[i].s2, (u32)recs[i].lam, ctr);
+    }
+}
+
+// Folds the exported tables of other devices into this one (the collection stage of reference
+// mpi.py:296-332 as one launch): payload j = header hdrs[j] (record count in key[0]) + records
+// recs[j * cap ...], written into this device's memory by the peers' export kernels.  A payload
+// that did not fit (count > cap) is skipped as a whole; the host sees the count and asks again.
+extern "C" __global__ void bsi_table_merge_payloads(BsiSlot *table, u32 log2_slots, const BsiRec *hdrs,
+                                                    const BsiRec *recs, u32 n_payloads, u64 cap,
+                                                    BsiCounters *ctr) {
+    for (u32 j = 0; j < n_payloads; ++j) {
+        const u64 count = hdrs[j].key[0];
+        if (count > cap) continue;
+        const BsiRec *r = recs + (u64)j * cap;
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64)gridDim.x * blockDim.x) {
+            if (r[i].n == 0ull) continue;
+            u64 key[BSI_KW];
+#pragma unroll
+            for (int k = 0; k < BSI_KW; ++k) key[k] = r[i].key[k];
+            bsi_table_add(table, log2_slots, key, r[i].n, r[i].s1, r[i].s2, (u32)r[i].lam, ctr);
+        }
     }
 }
 
@@ -1412,6 +1766,19 @@ bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lane
         BSI_STORE(b, t)
     }
 #undef BSI_STORE
+}
+
+// Node activity of attractors (reference attractor_analysis.py:49-51: the mean of every node over the
+// states of the cycle): block a counts, for every node, the states of orbit a in which it is on.
+// states: state codes [..][KW]; orbit a = states[start[a] .. start[a] + lam[a]).
+extern "C" __global__ void bsi_orbit_counts(const u64 *states, const u64 *start, const u64 *lam, u64 *counts) {
+    const u64 a = blockIdx.x;
+    const u64 s0 = start[a], n = lam[a];
+    for (u32 node = threadIdx.x; node < (u32)BSI_N; node += blockDim.x) {
+        u64 c = 0;
+        for (u64 t = 0; t < n; ++t) c += (states[(s0 + t) * BSI_KW + (node >> 6)] >> (node & 63u)) & 1ull;
+        counts[a * BSI_N + node] = c;
+    }
 }
 
 #if BSI_MODE == 2

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define BSI_ABI_VERSION 1
+#define BSI_ABI_VERSION 2
 #define BSI_KEY_WORDS_MAX 4               /* 64-bit words per state code: n_nodes <= 256 */
 #define BSI_INF UINT64_MAX                /* "no cap" for max_t, max_attractor_l, n_to_find */
 
@@ -114,7 +114,8 @@ typedef struct bsi_plan_opts {
     uint32_t filter_nodes;     /* attract: #nodes in the cheap pre-compare; 0 = auto (12) */
     uint32_t table_log2_slots; /* attract: device hash table size; 0 = auto (20) */
     uint32_t chunk_log2;       /* problems per launch wave; 0 = auto (26) */
-    uint32_t keep_source;      /* unused: the generated source is always kept */
+    uint32_t no_dict;          /* attract: 1 = no cycle dictionary (every matched lane walks its cycle for the
+                                  canonical key; for comparison only) */
     uint32_t block_threads;    /* threads per block of the trajectory kernels; 0 = auto (64) */
     uint32_t min_blocks;       /* __launch_bounds__ min blocks per SM (register cap); 0 = auto (1) */
     uint32_t debug_stats;      /* 1: count filter events (stats->reserved[0] = stage-2 filter entries,
@@ -128,7 +129,9 @@ typedef struct bsi_plan_opts {
                                   2 with min_blocks 6 buys a third warp per scheduler at N = 64 */
     uint32_t source_only;      /* offline plans only: 1 = generate the specialised source (bsi_plan_source,
                                   bsi_plan_op_counts) and skip NVRTC; the plan has no cubin */
-    uint32_t reserved[4];
+    uint32_t keep_dict;        /* attract: 1 = bsi_attract_table_clear leaves the cycle dictionary as it is (it
+                                  holds facts about the network's dynamics, not results) */
+    uint32_t reserved[3];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */
@@ -255,6 +258,13 @@ int bsi_attractor_states(bsi_plan *plan, const uint64_t *key, uint64_t lambda, u
 int bsi_attractor_states_batch(bsi_plan *plan, const uint64_t *keys, uint64_t n, uint64_t n_states,
                                uint64_t *out);
 
+/* Node activity of attractors (attractor_analysis.py:49-51: each attractor as an observation in [0,1]^N):
+ * counts[i][node] = number of states of attractor i's cycle in which `node` is on (its mean activity is
+ * counts / lambda).  Counted on the device from the orbits -- the ones the run stored, else regenerated.
+ * keys[n][key_words], lams[n] in; counts[n][n_nodes] out.  HOST buffers. */
+int bsi_attractor_activity(bsi_plan *plan, const uint64_t *keys, const uint64_t *lams, uint64_t n,
+                           uint64_t *counts);
+
 /* ---- simulate (replaces simulate_master's simulation stage, simulate.py:46-78) ------------- */
 /* states_out (HOST): [idx_end - idx_begin][max_t + 1][key_words], plain iteration with masks. */
 int bsi_simulate_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
@@ -272,6 +282,37 @@ int bsi_simulate_list(bsi_plan *plan, const uint64_t *indices, uint64_t n, uint6
 int bsi_target_run(bsi_plan *plan, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
                    uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,
                    bsi_run_stats *stats);
+
+/* ---- groups: one plan per device in ONE host process (replaces the MPI task farm, mpi.py:193-340) */
+/*
+ * A group holds one plan per device for the same network / space / mode (kernels are specialised once
+ * and loaded on every device).  Its run functions split [idx_begin, idx_end) into contiguous,
+ * word-aligned slices, one per device, and drive every device from its own host thread:
+ *  - attract: afterwards member 0's table holds the WHOLE job (read it with bsi_group_plan(g, 0) and
+ *    bsi_attract_table_read / bsi_attractor_states_batch).  The collection stage (mpi.py:296-332) is
+ *    the peers' export kernels writing their compacted tables into device 0's memory over NVLink and
+ *    one merge launch there; integer sums, so the result is bit-identical for any number of devices.
+ *    Tables start from empty on every call, and grow (job repeated) when the attractors do not fit.
+ *  - target: hits of all slices in index order, the first `cap` of them (simulate.py:163-164).
+ *  - simulate: every device writes its slice of the host output.
+ * devices == NULL: devices 0 .. n_devices-1; n_devices <= 0: every visible device.
+ */
+typedef struct bsi_group bsi_group;
+int bsi_group_create(const bsi_network_desc *network, const bsi_space_desc *space, int mode,
+                     const bsi_target_desc *target, const bsi_plan_opts *opts, const int *devices,
+                     int n_devices, bsi_group **out);
+void bsi_group_destroy(bsi_group *group);
+int bsi_group_size(const bsi_group *group, int *n_devices);
+/* Member i's plan, owned by the group. */
+int bsi_group_plan(bsi_group *group, int i, bsi_plan **plan);
+/* total: sums over the members (times: the slowest member); per_device: [n_devices] or NULL. */
+int bsi_group_attract_run(bsi_group *group, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                          uint64_t max_attractor_l, bsi_run_stats *total, bsi_run_stats *per_device);
+int bsi_group_target_run(bsi_group *group, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                         uint64_t *hit_index, uint64_t *hit_t, uint64_t cap, uint64_t *n_hits,
+                         bsi_run_stats *total);
+int bsi_group_simulate_run(bsi_group *group, uint64_t idx_begin, uint64_t idx_end, uint64_t max_t,
+                           uint64_t *states_out, bsi_run_stats *total);
 
 /* ---- measurement helpers (bench.py's roofline denominators; no reference counterpart) ------ */
 /* Integer-logic roofline microbenchmark: independent LOP3 chains on every SM of `device`;

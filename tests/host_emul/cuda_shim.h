@@ -1,6 +1,7 @@
 // Just enough of the CUDA execution model to run libbsi's kernel template on the host (test
-// infrastructure): one block of 32 threads = one warp = 32 host threads; warp collectives are
-// rendezvous on a barrier, atomics are the compiler's, shared memory is static storage.
+// infrastructure): one block of BSI_BLOCK threads = BSI_BLOCK / 32 warps of 32 host threads each (the
+// warps run independently, as on the device, so races between warps can show); warp collectives are
+// rendezvous on the warp's barrier, atomics are the compiler's, shared memory is static storage.
 // Every collective in the template is issued with the full mask at a warp-uniform point, so "all 32
 // threads meet at the barrier in the same order" is exactly the device's behaviour.
 #pragma once
@@ -35,11 +36,13 @@ static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 // ---- the warp ------------------------------------------------------------------------------------
-static pthread_barrier_t bsi_warp_barrier;
-static unsigned long long bsi_warp_slot[32];
-static inline void bsi_rendezvous() { pthread_barrier_wait(&bsi_warp_barrier); }
+#define BSI_EMUL_MAX_WARPS 8
+static pthread_barrier_t bsi_warp_barriers[BSI_EMUL_MAX_WARPS], bsi_block_barrier;
+static unsigned long long bsi_warp_slots[BSI_EMUL_MAX_WARPS][32];
+#define bsi_warp_slot bsi_warp_slots[threadIdx.x >> 5]
+static inline void bsi_rendezvous() { pthread_barrier_wait(&bsi_warp_barriers[threadIdx.x >> 5]); }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { bsi_rendezvous(); }
-static inline void __syncthreads() { bsi_rendezvous(); }
+static inline void __syncthreads() { pthread_barrier_wait(&bsi_block_barrier); }
 
 template <typename T>
 static inline T bsi_exchange(T v, int src) {
@@ -82,6 +85,33 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     for (int l = 0; l < 32; ++l) r += (unsigned)bsi_warp_slot[l];
     bsi_rendezvous();
     return r;
+}
+
+// one block of n_threads threads (a multiple of 32, at most 32 * BSI_EMUL_MAX_WARPS) runs `kernel`
+#include <functional>
+static inline void bsi_emul_block(unsigned n_threads, const std::function<void()> &kernel) {
+    const unsigned n_warps = n_threads / 32;
+    if (n_threads % 32 || n_warps == 0 || n_warps > BSI_EMUL_MAX_WARPS) { fprintf(stderr, "bad block size\n"); exit(9); }
+    blockDim.x = n_threads;
+    pthread_barrier_init(&bsi_block_barrier, nullptr, n_threads);
+    for (unsigned w = 0; w < n_warps; ++w) pthread_barrier_init(&bsi_warp_barriers[w], nullptr, 32);
+    struct Arg { const std::function<void()> *k; unsigned t; };
+    Arg *args = new Arg[n_threads];
+    pthread_t *th = new pthread_t[n_threads];
+    for (unsigned t = 0; t < n_threads; ++t) {
+        args[t] = {&kernel, t};
+        pthread_create(&th[t], nullptr, [](void *p) -> void * {
+            Arg *a = (Arg *)p;
+            threadIdx.x = a->t;
+            (*a->k)();
+            return nullptr;
+        }, &args[t]);
+    }
+    for (unsigned t = 0; t < n_threads; ++t) pthread_join(th[t], nullptr);
+    for (unsigned w = 0; w < n_warps; ++w) pthread_barrier_destroy(&bsi_warp_barriers[w]);
+    pthread_barrier_destroy(&bsi_block_barrier);
+    delete[] args;
+    delete[] th;
 }
 
 // ---- atomics / fences ----------------------------------------------------------------------------

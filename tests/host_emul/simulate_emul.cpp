@@ -22,20 +22,7 @@ static void launch(unsigned grid, const std::function<void()> &kernel) {
     gridDim.x = grid;
     for (unsigned blk = 0; blk < grid; ++blk) {
         blockIdx.x = blk;
-        pthread_barrier_init(&bsi_warp_barrier, nullptr, 32);
-        struct Arg { const std::function<void()> *k; unsigned lane; } args[32];
-        pthread_t th[32];
-        for (unsigned l = 0; l < 32; ++l) {
-            args[l] = {&kernel, l};
-            pthread_create(&th[l], nullptr, [](void *p) -> void * {
-                Arg *a = (Arg *)p;
-                threadIdx.x = a->lane;
-                (*a->k)();
-                return nullptr;
-            }, &args[l]);
-        }
-        for (unsigned l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
-        pthread_barrier_destroy(&bsi_warp_barrier);
+        bsi_emul_block(32, kernel);
     }
 }
 

@@ -27,7 +27,7 @@ def test_exports_match_header(built):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(raw, name), name
-    assert built.bsi_abi_version() == 1
+    assert built.bsi_abi_version() == 2
 
 
 def _pk(n, k, seed, n_free):

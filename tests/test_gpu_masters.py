@@ -33,6 +33,8 @@ def test_attract_master(case):
         assert att.states == [state_from_code(c, a['n_nodes']) for c in cyc]
         mean, m2 = oracle.mean_and_variation_sum(f, s1, s2)
         assert att.trajectory_l_mean == mean and att.trajectory_l_variation_sum == m2
+        # node activity counted on the device == what attractor_analysis.py:49-51 sums over the states
+        assert [int(c) for c in att.node_on_counts] == [sum(st[i] for st in att.states) for i in range(a['n_nodes'])]
     if want:
         assert sum(len(v) for v in db.root.aggregated_attractor_keys_by_batch_index.values()) == len(want)
 

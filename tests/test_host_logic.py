@@ -152,3 +152,53 @@ def test_problem_decoder_masks_equal_the_full_decode():
         for index in range(count_simulation_problems(variations)):
             _, fixed, perturbed = decode_simulation_problem(index, origin, variations)
             assert decoder.masks(index) == (fixed, perturbed), (variations, index)
+
+
+def _gloo_hits_worker(rank, world, port, n_to_find, out_dir):
+    import torch.distributed as dist
+    from boolsi_b200.target import exchange_hits, merge_sharded_hits
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    cfg = synth.random_target_problem(24, 3, 1, n_free=11, n_fixed=2, n_perturbed=2, n_perturbation_times=3,
+                                      max_perturbation_t=9, n_target_nodes=3)
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    lo, hi = problems.shard_range(sp.n_problems, rank, world)
+    if rank == 1:
+        hi = lo                     # an empty shard: a rank with no hits still takes part
+    sub = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 60, lo, hi)
+    hits = np.nonzero(sub['reached'])[0]
+    keep = hits if n_to_find == inf else hits[:n_to_find]
+    everyone = exchange_hits((keep + lo).astype(np.uint64), sub['stop_t'][keep], len(hits), sub['steps'], world, 'cpu')
+    index, t, total = merge_sharded_hits(everyone, n_to_find)
+    np.save(os.path.join(out_dir, 'h%d.npy' % rank), np.array([index.tolist(), t.tolist(), [total]], dtype=object),
+            allow_pickle=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_to_find', [inf, 5])
+def test_three_rank_hit_exchange_over_gloo(tmp_path, n_to_find):
+    """`target_sharded`'s exchange: fixed-size integer records through all_gather_into_tensor (no pickled
+    objects), ragged per-rank counts and an empty rank included; every rank ends with the same list."""
+    import torch.multiprocessing as mp
+    world = 3
+    port = 31500 + (os.getpid() + (0 if n_to_find == inf else 7)) % 2000
+    mp.spawn(_gloo_hits_worker, args=(world, port, n_to_find, str(tmp_path)), nprocs=world, join=True)
+    cfg = synth.random_target_problem(24, 3, 1, n_free=11, n_fixed=2, n_perturbed=2, n_perturbation_times=3,
+                                      max_perturbation_t=9, n_target_nodes=3)
+    sp = coracle.Space(cfg['incoming node lists'], cfg['truth tables'],
+                       cfg['origin simulation problem'], cfg['simulation problem variations'])
+    want_idx, want_t = [], []
+    for r in (0, 2):                                   # rank 1's shard was left out on purpose
+        lo, hi = problems.shard_range(sp.n_problems, r, world)
+        sub = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 60, lo, hi)
+        hits = np.nonzero(sub['reached'])[0]
+        want_idx += [int(i) + lo for i in hits]
+        want_t += [int(sub['stop_t'][i]) for i in hits]
+    total = len(want_idx)
+    if n_to_find != inf:
+        # each rank keeps its first n, the merge keeps the first n overall
+        want_idx, want_t = want_idx[:n_to_find], want_t[:n_to_find]
+    for r in range(world):
+        index, t, tot = np.load(os.path.join(str(tmp_path), 'h%d.npy' % r), allow_pickle=True).tolist()
+        assert [int(i) for i in index] == want_idx and [int(x) for x in t] == want_t and tot == [total]

@@ -24,8 +24,8 @@ REPO = os.path.dirname(HERE)
 pytestmark = pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
 
 
-def _build(tmp_path, packed, **opts):
-    with _lib.Plan(packed, _lib.MODE_ATTRACT, offline=True, block_threads=32, source_only=1, **opts) as plan:
+def _build(tmp_path, packed, block_threads=32, **opts):
+    with _lib.Plan(packed, _lib.MODE_ATTRACT, offline=True, block_threads=block_threads, source_only=1, **opts) as plan:
         header = plan.source().split('#line 1 "bsi_template.cuh"')[0]
     (tmp_path / 'header.h').write_text(header)
     exe = str(tmp_path / 'kernel_emul')
@@ -38,10 +38,11 @@ def _build(tmp_path, packed, **opts):
     return exe
 
 
-def _run(exe, lo, hi, max_t, max_a, first_horizon=0, few_words=0, no_early=0, table_log2=12):
+def _run(exe, lo, hi, max_t, max_a, first_horizon=0, few_words=0, no_early=0, table_log2=12, no_dict=0,
+         dict_log2=12):
     cap = lambda x: 0 if x == inf else int(x)            # noqa: E731  (0 = no cap on the command line)
     out = subprocess.run([exe] + [str(int(v)) for v in (lo, hi, cap(max_t), cap(max_a), first_horizon, few_words,
-                                                         no_early, table_log2)],
+                                                         no_early, table_log2, no_dict, dict_log2)],
                          capture_output=True, text=True, timeout=600, check=True).stdout.splitlines()
     head = out[0].split()
     counters = dict(steps=int(head[1]), accepted=int(head[2]), without=int(head[3]), table_full=int(head[4]),
@@ -292,3 +293,22 @@ def test_emulated_kernels_with_thousands_of_attractors(run_opts, tmp_path):
     want_rows, _, _ = _oracle(space, 50, inf, 0, pk.n_problems)
     assert len(want_rows) == 2560
     _check(exe, space, 0, pk.n_problems, 50, inf, table_log2=14, **run_opts)
+
+
+@pytest.mark.parametrize('block_threads', [32, 128])
+def test_emulated_cycle_dictionary(block_threads, tmp_path):
+    """Seed-1 network of the bench family (every trajectory ends in one of seven cycles of length 14,
+    29 or 58): throughput-mode resolution with the cycle dictionary -- learnt by the first words,
+    looked up by the rest; several independent warps, so that lookups race with a learner -- on,
+    off, and with orbit storage for two of the seven attractors only.  The harness also checks
+    that every stored orbit starts at its minimum state."""
+    cfg = synth.random_attract_problem(64, 3, 1, n_free=12)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk, block_threads=block_threads)
+    for opts in (dict(few_words=1), dict(few_words=1, no_early=1), dict(few_words=1, no_dict=1),
+                 dict(few_words=1, dict_log2=6), dict(few_words=1, first_horizon=8), {}):
+        _check(exe, space, 0, pk.n_problems, 1000, inf, **opts)
+    _check(exe, space, 100, 3001, 90, 30, few_words=1)
