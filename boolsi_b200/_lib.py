@@ -35,7 +35,7 @@ EXPORTS = [
     'bsi_measure_update_rate', 'bsi_release_cached_memory', 'bsi_attract_table_export_payload',
     'bsi_attractor_states_batch', 'bsi_attract_schedule', 'bsi_attract_run_async',
     'bsi_attract_run_finish', 'bsi_group_create', 'bsi_group_destroy', 'bsi_group_size', 'bsi_group_plan',
-    'bsi_group_attract_run', 'bsi_group_target_run', 'bsi_group_simulate_run', 'bsi_attractor_activity',
+    'bsi_group_attract_run', 'bsi_group_target_run', 'bsi_group_simulate_run', 'bsi_attractor_activity', 'bsi_attractor_orbits', 'bsi_plan_set_progress',
 ]
 
 
@@ -70,7 +70,7 @@ class PlanOpts(C.Structure):
                 ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
                 ('resolve_few_words', C.c_uint32), ('no_early_words', C.c_uint32),
                 ('smem_slots', C.c_uint32), ('source_only', C.c_uint32), ('keep_dict', C.c_uint32),
-                ('reserved', C.c_uint32 * 3)]
+                ('tune', C.c_uint32), ('reserved', C.c_uint32 * 2)]
 
 
 class RunStats(C.Structure):
@@ -85,6 +85,8 @@ class RunStats(C.Structure):
             d['debug'] = list(self.reserved[:4])
         return d
 
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_uint64, C.c_void_p)
 
 ATTRACTOR_REC = np.dtype([('key', np.uint64, (KEY_WORDS_MAX,)), ('n', np.uint64),
                           ('sum_l', np.uint64), ('sum_l2', np.uint64), ('lam', np.uint64)])
@@ -114,6 +116,7 @@ def lib():
         L.bsi_plan_n_problems.argtypes = [p, C.POINTER(u64)]
         L.bsi_plan_key_words.argtypes = [p, C.POINTER(u32)]
         L.bsi_plan_set_stream.argtypes = [p, p]
+        L.bsi_plan_set_progress.argtypes = [p, PROGRESS_FN, p]
         L.bsi_plan_source.argtypes = [p]
         L.bsi_plan_source.restype = C.c_char_p
         L.bsi_plan_build_log.argtypes = [p]
@@ -136,6 +139,7 @@ def lib():
         L.bsi_attractor_states.argtypes = [p, p, u64, p]
         L.bsi_attractor_states_batch.argtypes = [p, p, u64, u64, p]
         L.bsi_attractor_activity.argtypes = [p, p, p, u64, p]
+        L.bsi_attractor_orbits.argtypes = [p, p, p, u64, p, p]
         L.bsi_simulate_run.argtypes = [p, u64, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_simulate_list.argtypes = [p, p, u64, u64, p, C.POINTER(RunStats)]
         L.bsi_target_run.argtypes = [p, u64, u64, u64, p, p, u64, C.POINTER(u64),
@@ -364,6 +368,11 @@ class Plan:
         check(lib().bsi_measure_update_rate(self._h, C.byref(w), C.byref(l)))
         return {'word_steps_per_s': w.value, 'lop3_per_s': l.value}
 
+    def set_progress(self, callback):
+        """`callback(done, total)` after every finished wave of problems of a long run (None: off)."""
+        self._progress = PROGRESS_FN((lambda done, total, _user: callback(done, total))) if callback else PROGRESS_FN()
+        check(lib().bsi_plan_set_progress(self._h, self._progress, None))
+
     def set_stream(self, cuda_stream):
         check(lib().bsi_plan_set_stream(self._h, C.c_void_p(cuda_stream)))
 
@@ -451,6 +460,26 @@ class Plan:
                 out[pos] = buf[row, :lam].copy() if as_words else [code_from_words(w) for w in buf[row, :lam]]
         return out
 
+    def attractor_orbits(self, keys_and_lams, with_activity=False):
+        """[(key, lam), ...] -> list of uint64 arrays [lam, key_words] (key state first, attract.py:22-25),
+        one library call: orbits the run stored are copied, the others are entered into the cycle
+        dictionary first.  `with_activity`: also -> uint64 array [n, n_nodes], in how many states of each
+        cycle every node is on (counted on the device in the same pass)."""
+        n = len(keys_and_lams)
+        counts = np.zeros((n, self.packed.n_nodes), np.uint64) if with_activity else None
+        if not n:
+            return ([], counts) if with_activity else []
+        keys = np.zeros((n, self.kw), np.uint64)
+        for row, (key, _) in enumerate(keys_and_lams):
+            keys[row] = words_from_code(int(key), self.kw)
+        lams = np.array([int(lam) for _, lam in keys_and_lams], np.uint64)
+        ends = np.cumsum(lams.astype(np.int64))
+        states = np.zeros((int(ends[-1]), self.kw), np.uint64)
+        check(lib().bsi_attractor_orbits(self._h, _ptr(keys), _ptr(lams), n, _ptr(states),
+                                         _ptr(counts) if with_activity else None))
+        orbits = [states[int(e - l):int(e)] for e, l in zip(ends, lams.astype(np.int64))]
+        return (orbits, counts) if with_activity else orbits
+
     def attractor_activity(self, keys_and_lams):
         """[(key, lam), ...] -> uint64 array [n, n_nodes]: in how many states of each cycle every node
         is on (attractor_analysis.py:49-51 divides by the cycle length), counted on the device."""
@@ -535,6 +564,15 @@ class Group:
         h = C.c_void_p()
         check(lib().bsi_group_plan(self._h, int(i), C.byref(h)))
         return Plan.borrowed(h, self.packed, self.mode)
+
+    def set_progress(self, callback):
+        """`callback(member, done, total)` after every finished wave of problems on a member (called from
+        that member's host thread; None: off)."""
+        self._progress_plans = []
+        for i in range(self.n_devices):
+            member = self.plan(i)
+            member.set_progress((lambda done, total, i=i: callback(i, done, total)) if callback else None)
+            self._progress_plans.append(member)          # (keeps the ctypes callbacks alive)
 
     def attract_run(self, idx_begin, idx_end, max_t=inf, max_attractor_l=inf):
         """-> (totals, [per-device stats]); afterwards `plan(0)` holds the whole job's table."""

@@ -9,6 +9,7 @@ MPI task farm (mpi.py):
     runs under torchrun): per-GPU tables merged by one NCCL all_gather.
 """
 import logging
+import time
 from collections import OrderedDict
 from fractions import Fraction
 from math import inf
@@ -69,20 +70,36 @@ class AttractEngine:
             self.totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
             return st
         # kernels, table export and the collective are enqueued back to back; the first host
-        # synchronisation is the read of the gathered headers
-        self.plan.attract_run_async(self.lo, self.hi, max_t, max_attractor_l)
-        self.totals = self._merge_over_ranks()
+        # synchronisation is the read of the gathered headers.  A rank whose run fails still takes
+        # part in the collective (its header carries an error mark), so that the others do not wait
+        # for it forever; every rank then raises.
+        failure = None
+        try:
+            self.plan.attract_run_async(self.lo, self.hi, max_t, max_attractor_l)
+        except _lib.BsiError as e:
+            failure = e
+        self.totals = self._merge_over_ranks(failure)
         st = self.plan.attract_run_finish()
         st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
         return st
 
-    def _merge_over_ranks(self):
+    def _merge_over_ranks(self, failure=None):
         from .sharding import exchange_tables
         if self._gather is None:
             self._gather = {}
-        everyone, headers = exchange_tables(
-            lambda buf: self.plan.table_export_payload(buf.data_ptr(), buf.shape[0]),
-            self.world, 'cuda', buffers=self._gather)
+
+        def fill(buf):
+            if failure is None:
+                self.plan.table_export_payload(buf.data_ptr(), buf.shape[0])
+            else:
+                buf.zero_()
+                buf[0, 5] = 2           # header word 5: 0 ok, 1 table overflow, 2 the run failed on this rank
+        everyone, headers = exchange_tables(fill, self.world, 'cuda', buffers=self._gather)
+        if failure is not None:
+            raise failure
+        if int(headers[:, 5].max()) >= 2:
+            bad = [r for r in range(self.world) if int(headers[r, 5]) >= 2]
+            raise _lib.BsiError(-2, 'the run failed on rank(s) %s' % bad)
         if int(headers[:, 5].max()):
             raise _lib.BsiError(-4, 'attractor table overflow on some rank (raise table_log2_slots)')
         # fold the OTHER ranks' records into this rank's table (header rows and unused rows have
@@ -134,21 +151,26 @@ def read_attractors(plan, n_nodes):
     rows = [(_lib.code_from_words(r['key'][:plan.kw]), int(r['n']), int(r['sum_l']), int(r['sum_l2']), int(r['lam']))
             for r in plan.table_read()]
     rows.sort(key=lambda x: (-x[1], x[0]))
-    orbits = plan.attractor_states_batch([(key, lam) for key, _, _, _, lam in rows], as_words=True)
-    counts = plan.attractor_activity([(key, lam) for key, _, _, _, lam in rows])
+    orbits, counts = plan.attractor_orbits([(key, lam) for key, _, _, _, lam in rows], with_activity=True)
     return [AggregatedAttractor(key, _lib.states_from_word_rows(words, n_nodes), n, s1, s2, on)
             for (key, n, s1, s2, lam), words, on in zip(rows, orbits, counts)]
 
 
 def attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
-                    simulation_problem_variations, max_t=inf, max_attractor_l=inf, devices=None, **plan_opts):
+                    simulation_problem_variations, max_t=inf, max_attractor_l=inf, devices=None, progress=None,
+                    **plan_opts):
     """Host structures in, host results out, ONE process: the index space is split over `devices`
-    (None = every visible GPU) by the library's group run; no torch, no launcher.
+    (None = every visible GPU) by the library's group run; no torch, no launcher.  `progress(member,
+    done, total)` is called after every finished wave of a member's problems (long runs).
     :return: dict with the sorted attractors and the job totals."""
     packed = _lib.PackedProblem(predecessor_node_lists, truth_tables, origin_simulation_problem,
                                 simulation_problem_variations)
     group = cached_group(packed, _lib.MODE_ATTRACT, devices, **plan_opts)
-    total, per_device = group.attract_run(0, packed.n_problems, max_t, max_attractor_l)
+    group.set_progress(progress)
+    try:
+        total, per_device = group.attract_run(0, packed.n_problems, max_t, max_attractor_l)
+    finally:
+        group.set_progress(None)
     plan = group.plan(0)
     attractors = read_attractors(plan, packed.n_nodes)
     h2d = sum(a.nbytes for a in packed.arrays.values()) + 8 * plan.kw * len(attractors)
@@ -223,8 +245,18 @@ def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_si
         init_attractor_db_structure(db_conn)
     if device is not None:
         devices = [device]
+    # progress of long runs into the log, at most once a second (the reference feeds a progress bar
+    # from its batch loop, utils.py:19-54 / mpi.py:164)
+    last = [time.monotonic()]
+
+    def report(member, done, total):
+        now = time.monotonic()
+        if now - last[0] >= 1.0:
+            last[0] = now
+            log.info('GPU {}: {} of its {} initial conditions done'.format(member, done, total))
     res = attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
-                          simulation_problem_variations, max_t, max_attractor_l, devices=devices)
+                          simulation_problem_variations, max_t, max_attractor_l, devices=devices,
+                          progress=report)
     log.info('Used {} GPU(s).'.format(res['n_devices']))
     root = db_conn.root
     keys = []

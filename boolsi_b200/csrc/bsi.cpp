@@ -11,6 +11,7 @@
 // simulate.py:97-178 (see include/bsi.h for the per-function citations).
 #include <cuda.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <nvrtc.h>
 
@@ -205,7 +206,7 @@ struct bsi_plan {
     CUstream own_stream = nullptr, stream = nullptr;
     CUfunction f_dense = nullptr, f_queue = nullptr, f_mu = nullptr, f_early = nullptr,
                f_resolve = nullptr, f_finish = nullptr,
-               f_export = nullptr, f_merge = nullptr, f_merge_payloads = nullptr, f_traj = nullptr, f_counts = nullptr,
+               f_export = nullptr, f_merge = nullptr, f_merge_payloads = nullptr, f_traj = nullptr, f_counts = nullptr, f_learn_keys = nullptr,
                f_target = nullptr;
     int n_sms = 0;
     int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
@@ -215,6 +216,8 @@ struct bsi_plan {
     DevBuf ctr, table, found_q, retry_q[2], scratch, early_q, misc, misc2, misc3, misc4, misc5;
     DevBuf dict_slots, dict_orbit, dict_dir, dict_ctr;     // cycle dictionary (attract)
     DictParam dict{};
+    bsi_progress_fn progress = nullptr;                    // reports finished problems of long runs
+    void *progress_user = nullptr;
     std::vector<CUevent> events;
     size_t events_used = 0;
     uint64_t launches = 0;
@@ -424,18 +427,34 @@ struct CachedUnit {
 std::mutex g_unit_mu;
 std::map<std::pair<std::string, int>, CachedUnit> g_units;
 
-// Optional second level on disk, for the NEXT process that runs the same network (NVRTC takes a
-// few seconds per network, a 2^30-state cambium run 50 ms): off unless BSI_CACHE_DIR names a
-// directory.  One file per unit, named by a hash of (header, template, NVRTC version, unit); the
+// Second level on disk, for the NEXT process that runs the same network (NVRTC takes a few seconds
+// per network, a 2^30-state cambium run 50 ms): on by default in the user's cache directory.  One file per unit, named by a hash of (header, template, NVRTC version, unit); the
 // file repeats the header, which is compared on load, so a hash collision cannot hand out the
 // wrong kernels.  Written to a temporary name and renamed: readers never see a partial file.
 uint64_t fnv1a(const std::string &text, uint64_t h = 0xCBF29CE484222325ull) {
     for (unsigned char c : text) { h ^= c; h *= 0x100000001B3ull; }
     return h;
 }
-std::string disk_cache_path(const std::string &header, int unit) {
+// The cache directory: BSI_CACHE_DIR if set ("" or "off" switch the disk level off), else
+// $XDG_CACHE_HOME/boolsi_b200, else ~/.cache/boolsi_b200 (created on first use; an unwritable or
+// missing home simply means no disk level).
+std::string disk_cache_dir() {
     const char *dir = getenv("BSI_CACHE_DIR");
-    if (!dir || !*dir) return std::string();
+    if (dir) return (!*dir || !strcmp(dir, "off")) ? std::string() : std::string(dir);
+    std::string base;
+    const char *xdg = getenv("XDG_CACHE_HOME"), *home = getenv("HOME");
+    if (xdg && *xdg) base = xdg;
+    else if (home && *home) base = std::string(home) + "/.cache";
+    else return std::string();
+    mkdir(base.c_str(), 0755);
+    base += "/boolsi_b200";
+    mkdir(base.c_str(), 0755);
+    return base;
+}
+std::string disk_cache_path(const std::string &header, int unit) {
+    const std::string dir_s = disk_cache_dir();
+    const char *dir = dir_s.c_str();
+    if (dir_s.empty()) return std::string();
     int major = 0, minor = 0;
     nvrtcVersion(&major, &minor);
     uint64_t h = fnv1a(header);
@@ -513,10 +532,17 @@ int compile_plan(bsi_plan *p) {
     // step) but 7 % slower when 13 % of the lanes close (seed 2: the match handlers spill).  Not the
     // default; both knobs stay for tuning.
     const int min_blocks = p->opts.min_blocks ? (int)p->opts.min_blocks : 1;
+    // Cycles up to this length are walked by the resolution kernels, longer ones looked up in the cycle
+    // dictionary: the key walk + advance of a word cost about (2 U + 4 N) LOP3 per step of its longest
+    // cycle, 32 lookups + gathers + the 32x32 transposes about 2800 instructions.
+    const int walk_per_step = 2 * std::max(1, p->m.n) + 4 * p->m.n;      // (U <= N for K <= 3; a bound is enough)
+    const int dict_min_lam = std::max(8, 2800 / walk_per_step);
     p->smem_slots = p->opts.smem_slots ? (int)p->opts.smem_slots : 3;
     if (p->smem_slots < 1 || p->smem_slots > 3) return fail(BSI_E_ARG, "smem_slots must be 1, 2 or 3");
     const std::string header = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info) +
-                               "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n";
+                               "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n" +
+                               "#define BSI_DICT_MIN_LAM " + std::to_string(dict_min_lam) + "u\n" +
+                               "#define BSI_TUNE " + std::to_string(p->opts.tune) + "\n";
     p->source = header + "\n#line 1 \"bsi_template.cuh\"\n" + bsi_template_src;
     tm.lap("generate source");
     if (p->opts.source_only) {                             // inspection / host emulation: no NVRTC
@@ -628,6 +654,7 @@ int load_plan(bsi_plan *p, int device) {
         CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
         CU_CHECK(cuModuleGetFunction(&p->f_resolve, p->mods[5], "bsi_resolve"));
         CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
+        CU_CHECK(cuModuleGetFunction(&p->f_learn_keys, p->mods[3], "bsi_dict_learn_keys"));
         CU_CHECK(cuModuleGetFunction(&p->f_early, p->mods[6], "bsi_resolve_early"));
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
@@ -820,6 +847,13 @@ int bsi_plan_n_problems(const bsi_plan *p, uint64_t *n) {
 int bsi_plan_key_words(const bsi_plan *p, uint32_t *kw) {
     if (!p || !kw) return fail(BSI_E_ARG, "null pointer");
     *kw = (uint32_t)p->m.kw;
+    return BSI_OK;
+}
+
+int bsi_plan_set_progress(bsi_plan *p, bsi_progress_fn fn, void *user) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    p->progress = fn;
+    p->progress_user = user;
     return BSI_OK;
 }
 
@@ -1026,6 +1060,8 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
             else H = std::min(H * 4, kMaxH);
         }
         b = e;
+        // (with several rounds per chunk the host has waited for this chunk: it is finished)
+        if (p->progress) p->progress(b - idx_begin, idx_end - idx_begin, p->progress_user);
     }
     CU_CHECK(cuEventRecord(tm.e1, p->stream));
     p->pending = true;
@@ -1333,6 +1369,73 @@ int bsi_attractor_states_batch(bsi_plan *p, const uint64_t *keys, uint64_t n, ui
     return BSI_OK;
 }
 
+int bsi_attractor_orbits(bsi_plan *p, const uint64_t *keys, const uint64_t *lams, uint64_t n,
+                         uint64_t *states, uint64_t *counts) {
+    int rc = need_device(p, BSI_MODE_ATTRACT);
+    if (rc) return rc;
+    if (n == 0) return BSI_OK;
+    if (!keys || !lams || !states) return fail(BSI_E_ARG, "null pointer");
+    CtxGuard g(p);
+    const uint64_t kw = (uint64_t)p->m.kw, nn = (uint64_t)p->m.n;
+    std::vector<uint64_t> offset(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (lams[i] == 0) return fail(BSI_E_ARG, "attractor length 0");
+        offset[i + 1] = offset[i] + lams[i];
+    }
+    std::vector<uint64_t> bases(n, ~0ull), host_counts;
+    if (p->dict.slots) {
+        // one pass on the device: find or store every orbit (bases), count node activity where the orbits
+        // lie -- two launches, no host round trip between them
+        if ((rc = ensure(p, p->misc4, 8 * n * (kw + 2))) || (counts && (rc = ensure(p, p->misc5, 8 * n * nn)))) return rc;
+        CUdeviceptr d_keys = p->misc4.p, d_lams = d_keys + 8 * n * kw, d_bases = d_lams + 8 * n;
+        CU_CHECK(cuMemcpyHtoDAsync(d_keys, keys, 8 * n * kw, p->stream));
+        CU_CHECK(cuMemcpyHtoDAsync(d_lams, lams, 8 * n, p->stream));
+        uint64_t nk = n;
+        void *args[] = {&d_keys, &d_lams, &nk, &d_bases, &p->dict};
+        // (one thread per block: the threads of a warp would walk their orbits one after the other)
+        if ((rc = launch(p, p->f_learn_keys, (unsigned)n, 32, 0, args))) return rc;
+        if (counts) {
+            void *cargs[] = {&p->dict_orbit.p, &d_bases, &d_lams, &p->misc5.p};
+            if ((rc = launch(p, p->f_counts, (unsigned)n, 128, 0, cargs))) return rc;
+            host_counts.resize(n * nn);
+            CU_CHECK(cuMemcpyDtoHAsync(host_counts.data(), p->misc5.p, 8 * n * nn, p->stream));
+        }
+        CU_CHECK(cuMemcpyDtoHAsync(bases.data(), d_bases, 8 * n, p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+        // the stored orbits: one copy of the range that holds them
+        uint64_t lo = ~0ull, hi = 0;
+        for (uint64_t i = 0; i < n; ++i)
+            if (bases[i] != ~0ull) { lo = std::min(lo, bases[i]); hi = std::max(hi, bases[i] + lams[i]); }
+        if (hi > lo) {
+            std::vector<uint64_t> orbit((hi - lo) * kw);
+            CU_CHECK(cuMemcpyDtoHAsync(orbit.data(), p->dict_orbit.p + 8 * lo * kw, 8 * (hi - lo) * kw, p->stream));
+            CU_CHECK(cuStreamSynchronize(p->stream));
+            for (uint64_t i = 0; i < n; ++i)
+                if (bases[i] != ~0ull)
+                    memcpy(states + offset[i] * kw, orbit.data() + (bases[i] - lo) * kw, 8 * kw * lams[i]);
+        }
+    }
+    // fixed points are their own orbit; what the dictionary could not take (storage exhausted, dictionary
+    // off) is regenerated by the trajectory kernel and counted with bsi_attractor_activity's fallback
+    std::vector<uint64_t> rest;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (bases[i] != ~0ull) {
+            if (counts) memcpy(counts + i * nn, host_counts.data() + i * nn, 8 * nn);
+        } else if (lams[i] == 1) {
+            memcpy(states + offset[i] * kw, keys + i * kw, 8 * kw);
+            if (counts) for (uint64_t v = 0; v < nn; ++v) counts[i * nn + v] = (keys[i * kw + (v >> 6)] >> (v & 63)) & 1;
+        } else {
+            rest.push_back(i);
+        }
+    }
+    for (uint64_t i : rest) {
+        if ((rc = run_trajectories(p, 0, nullptr, keys + i * kw, 1, lams[i] - 1, states + offset[i] * kw, nullptr)))
+            return rc;
+        if (counts && (rc = bsi_attractor_activity(p, keys + i * kw, lams + i, 1, counts + i * nn))) return rc;
+    }
+    return BSI_OK;
+}
+
 int bsi_attractor_activity(bsi_plan *p, const uint64_t *keys, const uint64_t *lams, uint64_t n,
                            uint64_t *counts) {
     int rc = need_device(p, BSI_MODE_ATTRACT);
@@ -1416,6 +1519,9 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
     if (rc) return rc;
     if (idx_begin > idx_end || idx_end > p->m.n_problems) return fail(BSI_E_ARG, "bad index range");
     if (cap && (!hit_index || !hit_t)) return fail(BSI_E_ARG, "null hit buffers");
+    // (hit times and last-perturbation times travel as 32-bit words on the device)
+    if (max_t != BSI_INF && max_t >= ((uint64_t)1 << 32)) return fail(BSI_E_ARG, "target: a finite max_t must be below 2^32");
+    if (p->m.lp_max >= ((uint64_t)1 << 32)) return fail(BSI_E_UNSUPPORTED, "target: perturbation times of 2^32 and up are not supported");
     CtxGuard g(p);
     bsi_run_stats st{};
     st.n_problems = idx_end - idx_begin;
@@ -1485,6 +1591,7 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
             ++written;
         }
         b = e;
+        if (p->progress) p->progress(b - idx_begin, idx_end - idx_begin, p->progress_user);
     }
     CU_CHECK(cuEventRecord(e1, p->stream));
     Counters c;

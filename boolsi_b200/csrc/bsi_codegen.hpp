@@ -479,6 +479,10 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         o << " }\n#define BSI_CMP_FILTER2B_MEM(acc, X, P, S) {";
         for (size_t g = tier_a; g < filter2.size(); ++g)
             o << " acc = bsi_lop3<0xF6>(acc, X##" << filter2[g] << ", (P)[" << filter2[g] << " * (S)]);";
+        // full compare of a register state against a checkpoint in memory: one load + one lop3 per node
+        o << " }\n#define BSI_CMP_ALL_MEM(acc, X, P, S) {";
+        for (int i = 0; i < n; ++i)
+            o << " acc = bsi_lop3<0xF6>(acc, X##" << i << ", (P)[" << i << " * (S)]);";
         o << " }\n#define BSI_STORE_ALL(X, P, S) {";
         for (int i = 0; i < n; ++i) o << " (P)[" << i << " * (S)] = X##" << i << ";";
         o << " }\n#define BSI_LOAD_MEM(X, P, S) {";
@@ -584,7 +588,7 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         o << "#define BSI_PACK(X, CW) { unsigned int A_[32];";
         for (int b = 0; b < blocks; ++b) {
             o << " _Pragma(\"unroll\") for (int k_ = 0; k_ < 32; ++k_) A_[k_] = (unsigned int)((CW)[31 - k_]["
-              << (b >> 1) << "] >> " << (32 * (b & 1)) << "); bsi_transpose32(A_);";
+              << (b >> 1) << "] >> " << (32 * (b & 1)) << "); BSI_TRANSPOSE32(A_);";
             for (int i = 0; i < 32 && 32 * b + i < n; ++i)
                 o << " X##" << (32 * b + i) << " = A_[" << (31 - i) << "];";
         }
@@ -595,7 +599,7 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
                 if (node < n) o << " A_[" << k << "] = X##" << node << ";";
                 else o << " A_[" << k << "] = 0u;";
             }
-            o << " bsi_transpose32(A_); _Pragma(\"unroll\") for (int k_ = 0; k_ < 32; ++k_) (CW)[31 - k_]["
+            o << " BSI_TRANSPOSE32(A_); _Pragma(\"unroll\") for (int k_ = 0; k_ < 32; ++k_) (CW)[31 - k_]["
               << (b >> 1) << "] " << ((b & 1) ? "|= (unsigned long long)A_[k_] << 32;" : "= (unsigned long long)A_[k_];");
         }
         o << " }\n";

@@ -55,6 +55,9 @@ __device__ __forceinline__ u32 bsi_lop3(u32 a, u32 b, u32 c) {
 // 32x32 bit-matrix transpose in place (Hacker's Delight 7-3): B[r] bit c = A[31-c] bit 31-r.
 // Turns 32 node words (bit = lane) into 32 lane words (bit = node) and back in 5 x 16 butterfly
 // steps instead of 32 x 32 single-bit moves (BSI_PACK / BSI_UNPACK in the generated header).
+#ifndef BSI_TUNE
+#define BSI_TUNE 0
+#endif
 __device__ __forceinline__ void bsi_transpose32(unsigned int (&A)[32]) {
     unsigned int m = 0x0000FFFFu;
 #pragma unroll
@@ -67,6 +70,11 @@ __device__ __forceinline__ void bsi_transpose32(unsigned int (&A)[32]) {
         }
     }
 }
+
+// (BSI_TUNE bit 0: in the resolution kernels the transpose is a function call on a local-memory array,
+//  not ~400 inlined instructions per use: those kernels hold six to ten uses, most of their code)
+__device__ __noinline__ void bsi_transpose32_call(unsigned int (&A)[32]) { bsi_transpose32(A); }
+#define BSI_TRANSPOSE32(A) bsi_transpose32(A)
 
 struct BsiCounters {
     // reset before every round
@@ -184,6 +192,12 @@ __device__ __forceinline__ u64 bsi_hash_key(const u64 *k) {
         h *= 0xBF58476D1CE4E5B9ull;
         h ^= h >> 29;
     }
+    // (a product's low bits only see the low bits of its input: without this round, states that
+    //  differ in nodes 48 and up only -- half of the states of a typical cycle pair up that way --
+    //  shared a slot index, and every second lookup took the probe sequence instead of one load)
+    h ^= h >> 32;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 31;
     return h;
 }
 
@@ -288,7 +302,7 @@ __device__ __forceinline__ u64 bsi_ldcg_u64(const u64 *p) {
 }
 
 // state -> (idx, base, lambda); false on a miss (or on a slot that is still being written)
-__device__ __forceinline__ bool bsi_dict_find(const BsiDict &d, const u64 *st, u32 &idx, u32 &base, u32 &lam) {
+__device__ __noinline__ bool bsi_dict_find(const BsiDict &d, const u64 *st, u32 &idx, u32 &base, u32 &lam) {
     const u32 mask = (1u << d.log2_slots) - 1u;
     u32 pos = (u32)bsi_hash_key(st) & mask;
 #pragma unroll 1
@@ -515,17 +529,16 @@ __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 
 // (= the checkpoint itself) and the previous checkpoint are extracted from shared memory at the end
 // of the word, when all threads of the warp do so together instead of one diverged thread now.
 #define BSI_DEFERRED 0x80000000u
-// A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten)
-// latches the matched lanes' state bit-sliced: yl[i] takes the bits of xs[i] in the lanes of m.
-// One rolled pass over the nodes per event, however many lanes it has; the per-lane state codes
-// come out of one 32x32-transpose pass at the end of the word.
-__device__ __forceinline__ void bsi_record(const u32 *xs, u32 *yl, u32 m, u32 lam, u32 c, u32 *lam_s,
-                                           u32 *c_s, u64 sstride, u32 slot, bool deferred) {
+// A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten) is
+// only noted as well: the matched state IS the checkpoint's, so the matched lanes stay `pending`
+// and their bits are copied from slot 0 into the bit-sliced latch yl right before that slot is
+// overwritten (and at the end of the word) -- one pass over the nodes per CHECKPOINT that had
+// matches, not per match event (a word of the regime where every lane closes after a transient of
+// its own has up to 32 events but matches against a handful of checkpoints).  The per-lane state
+// codes come out of one 32x32-transpose pass at the end of the word.
+__device__ __forceinline__ void bsi_record(u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s, u64 sstride, u32 slot,
+                                           bool deferred) {
     u32 *c0_s = c_s + 32ull * sstride;
-    if (!deferred) {
-#pragma unroll 8
-        for (int i = 0; i < BSI_N; ++i) yl[i] = (yl[i] & ~m) | (xs[i] & m);
-    }
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
@@ -533,6 +546,11 @@ __device__ __forceinline__ void bsi_record(const u32 *xs, u32 *yl, u32 m, u32 la
         c_s[l * sstride] = c;
         c0_s[l * sstride] = deferred ? (BSI_DEFERRED | slot) : 0u;
     }
+}
+// yl <- slot 0's checkpoint in the lanes of m
+__device__ __forceinline__ void bsi_latch_pending(u32 *yl, const u32 *ck0, u64 cstride, u32 m) {
+#pragma unroll 8
+    for (int i = 0; i < BSI_N; ++i) yl[i] = (yl[i] & ~m) | (ck0[i * cstride] & m);
 }
 
 // DENSE: words of the contiguous index range [idx_begin, idx_end), word0 = idx_begin >> 5.
@@ -570,6 +588,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         BSI_FOR_FILTER(BSI_DECL_K1)
         BSI_FOR_FILTER(BSI_DECL_K2)
         u32 valid = 0u, F = 0u, alive = 0u, early = 0u;
+        u32 pend = 0u;                           // early-matched lanes whose state is still only in slot 0
         u32 st0 = 0, st1 = 0, st2 = 0;           // checkpoint time held by each slot
         u32 yl_[BSI_N];                          // bit-sliced latch of the early matches' states
 
@@ -619,9 +638,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             if (m_) {                                                                \
                 F |= m_;                                                             \
                 alive &= ~m_;                                                        \
-                bsi_record(XS, yl_, m_, (J) - (ST), (ST), lam_s, c_s, sstride, (S),  \
+                bsi_record(m_, (J) - (ST), (ST), lam_s, c_s, sstride, (S),           \
                            (S) > 0 || (ST) >= sched.first_final);                    \
-                if (!((S) > 0 || (ST) >= sched.first_final)) early |= m_;            \
+                if (!((S) > 0 || (ST) >= sched.first_final)) { early |= m_; pend |= m_; } \
             }                                                                        \
         }                                                                            \
     }
@@ -662,13 +681,23 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #define BSI_ANY3 (bsi_lop3<0x80>(p0, p1, p2) != 0xFFFFFFFFu)
             // slow handlers: stage 2, then the full compare of the surviving candidates
 #define BSI_SLOW0(X, J) {}
+            // (one slot armed -- the early phase, where whole words close lane by lane: the full
+            //  compare runs straight from the state registers, one LDS + one lop3 per node, no dump)
 #define BSI_SLOW1(X, J)                                                              \
     {                                                                                \
         BSI_STAGE2(X, 0, p0)                                                         \
         if (BSI_ANY1) {                                                              \
-            u32 xs_[BSI_N];                                                          \
-            BSI_DUMP(X, xs_)                                                         \
-            BSI_FULL(xs_, J, 0, st0, p0)                                             \
+            BSI_COUNT(1)                                                             \
+            u32 acc_ = p0 | ~alive;                                                  \
+            BSI_CMP_ALL_MEM(acc_, X, BSI_CK_PTR(0), BSI_CK_STRIDE(0))                \
+            const u32 m_ = ~acc_;                                                    \
+            if (m_) {                                                                \
+                const bool def_ = st0 >= sched.first_final;                          \
+                F |= m_;                                                             \
+                alive &= ~m_;                                                        \
+                bsi_record(m_, (J) - st0, st0, lam_s, c_s, sstride, 0u, def_);       \
+                if (!def_) { early |= m_; pend |= m_; }                              \
+            }                                                                        \
         }                                                                            \
     }
 #define BSI_SLOW2(X, J)                                                              \
@@ -735,6 +764,10 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 // checkpoint due at time j: state a (already compared) goes into its slot
                 if (ci < sched.n_ck && sched.ck_time[ci] == j) {
                     const u32 s = sched.ck_slot[ci];
+                    if (s == 0u && pend) {
+                        bsi_latch_pending(yl_, BSI_CK_PTR(0), BSI_CK_STRIDE(0), pend);
+                        pend = 0u;
+                    }
                     if (BSI_CK_ONCHIP(s)) {
                         u32 *p_ = ck_s + s * BSI_N * BSI_BLOCK;
                         BSI_STORE_ALL(a, p_, BSI_BLOCK)
@@ -763,6 +796,10 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         }
 
         // ---- results ------------------------------------------------------------------------------
+        if (pend) {
+            bsi_latch_pending(yl_, BSI_CK_PTR(0), BSI_CK_STRIDE(0), pend);
+            pend = 0u;
+        }
         const u32 matched = F;
         // early matches of a dense word -> early-word queue, bit-sliced as they are
         if (DENSE && early_cap) {
@@ -878,6 +915,10 @@ bsi_attract_queue(const u64 *in_queue, u64 n_in, const BsiSched sched, int final
 // ---------------------------------------------------------------------------------------------
 // attract: exact resolution of the matched lanes
 // ---------------------------------------------------------------------------------------------
+#if BSI_TUNE & 1
+#undef BSI_TRANSPOSE32
+#define BSI_TRANSPOSE32(A) bsi_transpose32_call(A)
+#endif
 #if BSI_UNIT == 0 || BSI_UNIT == 3 || BSI_UNIT == 5 || BSI_UNIT == 6
 
 // Which records of the found queue form "word" w of the resolution kernels: words come in groups
@@ -941,7 +982,7 @@ __device__ __forceinline__ void bsi_key_core(u64 (*cw_)[BSI_KW], u32 valid, u32 
 // advancing set one by one), a second pass of s steps then yields 32 states per step, so the 32x32
 // transposes that turn bit-sliced words into state codes are paid s times and not lam times.  Only
 // when the whole orbit is in memory are its states entered (read back from there), the key last.
-__device__ __noinline__ void bsi_dict_learn(const BsiDict &d, const u64 *key, u32 lam, u32 base, u32 slot) {
+__device__ __noinline__ void bsi_dict_store_orbit(const BsiDict &d, const u64 *key, u32 lam, u32 base) {
     BSI_FOR_NODES(BSI_DECL_A)
     BSI_FOR_NODES(BSI_DECL_B)
 #define BSI_BCAST_NODE(i) a##i = 0u - (u32)((key[(i) >> 6] >> ((i) & 63)) & 1ull);
@@ -970,13 +1011,21 @@ __device__ __noinline__ void bsi_dict_learn(const BsiDict &d, const u64 *key, u3
         BSI_FOR_NODES(BSI_COPY_AB)
     }
     __threadfence();
+}
+// enter the states of a stored orbit, phases first, first + stride, ... (the key state, phase 0, is there)
+__device__ __forceinline__ void bsi_dict_put_orbit(const BsiDict &d, u32 lam, u32 base, u32 first, u32 stride) {
 #pragma unroll 1
-    for (u32 ph = 1; ph < lam; ++ph) {
+    for (u32 ph = first; ph < lam; ph += stride) {
+        if (ph == 0u) continue;
         u64 st[BSI_KW];
 #pragma unroll
         for (int i = 0; i < BSI_KW; ++i) st[i] = bsi_ld_u64(&d.orbit[(u64)(base + ph) * BSI_KW + i]);
         bsi_dict_put(d, st, base + ph, base, lam);
     }
+}
+__device__ __noinline__ void bsi_dict_learn(const BsiDict &d, const u64 *key, u32 lam, u32 base, u32 slot) {
+    bsi_dict_store_orbit(d, key, lam, base);
+    bsi_dict_put_orbit(d, lam, base, 1u, 1u);
     bsi_dict_publish(d, slot);
 }
 
@@ -1027,12 +1076,12 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
     }
 }
 
-// Exact mu, then acceptance and aggregation.  With y = x_c on the cycle, let P be the periodic
-// extension of the cycle to all times: P(j) = x_j exactly for j >= mu, so for any c0 < mu
-//     mu = first j >= c0 with x_j == P(j),   P(c0) = y advanced by (lambda - (c - c0) mod lambda) mod lambda.
-// a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
-// walks P(j); three register sets rotate so that no step needs a copy.
-// Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
+// The dictionary's part of resolving one word, OUT OF LINE (the resolution kernels are big; what a
+// word of short cycles never executes must not sit in the instruction cache's way): look the matched
+// states ycw[l] of the lanes on cycles up -- eight independent probes in flight at a time -- and, if
+// the dictionary knows them ALL, fetch P(c0) = y advanced by adv[l] steps (pcode) and, with
+// want_keys, the canonical keys (keys[l]) from the stored orbits; pb receives P(c0) bit-sliced, one
+// word per node.  Returns the lanes it does not know (0: pb / keys are filled).
 struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it runs in the same kernel
     u64 key[32][BSI_KW];
     u32 lam[32], c0[32];
@@ -1040,7 +1089,80 @@ struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it
     // state -- the ordered regime's normal case.  Then only key[first valid lane] is filled.
     u32 uniform;
 };
+__device__ __noinline__ u32 bsi_dict_word(const BsiDict &dict, u64 (*ycw)[BSI_KW], const u32 *lam, const u32 *adv_s,
+                                          bool want_keys, u64 (*keys)[BSI_KW], u32 *pb) {
+    const u32 mask_ = (1u << dict.log2_slots) - 1u;
+    u32 dbase_[32], dphase_[32];
+    u32 miss = 0u;
+#pragma unroll 1
+    for (u32 l0 = 0; l0 < 32; l0 += 8) {
+        u32 f_[8], idx_[8], base_[8], lamd_[8];
+        u64 st_[8][BSI_KW];
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) {
+            const BsiDictSlot *s_ = dict.slots + ((u32)bsi_hash_key(ycw[l0 + k]) & mask_);
+            bsi_dict_head_cg(s_, f_[k], idx_[k], base_[k], lamd_[k]);
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) st_[k][i] = bsi_ldcg_u64(&s_->st[i]);
+        }
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) {
+            const u32 l = l0 + k;
+            if (lam[l] <= 1u) continue;
+            bool hit = f_[k] == 2u;
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) hit = hit && st_[k][i] == ycw[l][i];
+            // (not in its first slot: the full probe sequence)
+            if (!hit) hit = bsi_dict_find(dict, ycw[l], idx_[k], base_[k], lamd_[k]);
+            if (hit && lamd_[k] == lam[l]) {
+                dbase_[l] = base_[k];
+                dphase_[l] = idx_[k] - base_[k];
+            } else {
+                miss |= 1u << l;
+            }
+        }
+    }
+    if (miss) return miss;
+    u64 cp_[32][BSI_KW];
+#pragma unroll 1
+    for (u32 l0 = 0; l0 < 32; l0 += 8) {
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) {
+            const u32 l = l0 + k;
+            const u32 lm = lam[l];
+            if (lm > 1u) {
+                u32 ph = dphase_[l] + adv_s[l * BSI_BLOCK];
+                if (ph >= lm) ph -= lm;
+                const u64 *po = dict.orbit + (u64)(dbase_[l] + ph) * BSI_KW;
+                const u64 *pk = dict.orbit + (u64)dbase_[l] * BSI_KW;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) {
+                    cp_[l][i] = bsi_ldcg_u64(po + i);
+                    if (want_keys) keys[l][i] = bsi_ldcg_u64(pk + i);
+                }
+            } else {
+                // (fixed points: P is the state itself, and so is the key)
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) cp_[l][i] = lm ? ycw[l][i] : 0ull;
+            }
+        }
+    }
+    {
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_PACK(b, cp_)
+#define BSI_STORE_PB(i) pb[i] = b##i;
+        BSI_FOR_NODES(BSI_STORE_PB)
+#undef BSI_STORE_PB
+    }
+    return 0u;
+}
 
+// Exact mu, then acceptance and aggregation.  With y = x_c on the cycle, let P be the periodic
+// extension of the cycle to all times: P(j) = x_j exactly for j >= mu, so for any c0 < mu
+//     mu = first j >= c0 with x_j == P(j),   P(c0) = y advanced by (lambda - (c - c0) mod lambda) mod lambda.
+// a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
+// walks P(j); three register sets rotate so that no step needs a copy.
+// Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
 // EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in its y field, all
 // starting from the dense problem-index word in its word field, c0 = 0); otherwise word w of found_q.
 // `keep` always receives lambda and c0 of the lanes; with KEEP also their canonical keys (from the
@@ -1152,70 +1274,20 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         }
         // ---- lanes on cycles (lambda > 1): does the dictionary know every one of them? -----------
         u64 (*const ycw_)[BSI_KW] = EARLY ? keep->key : cw_;      // the matched states as codes
-        u32 dbase_[32], dphase_[32];
         u32 miss = 0u;
         bool use_dict = false;
-        if (lam_max > 1u) {
-            // (short cycles are walked: the key walk and the advance of a word take lam_max - 1 steps
-            //  each, which is cheaper than 32 lookups and two 32x32 transposes up to about 8 states)
-            if (dict.slots && lam_max > BSI_DICT_MIN_LAM) {
-                const u32 mask_ = (1u << dict.log2_slots) - 1u;
-#pragma unroll 1
-                for (u32 l0 = 0; l0 < 32; l0 += 8) {
-                    // eight independent probes in flight, then the compares
-                    u32 f_[8], idx_[8], base_[8], lamd_[8];
-                    u64 st_[8][BSI_KW];
-#pragma unroll
-                    for (u32 k = 0; k < 8; ++k) {
-                        const BsiDictSlot *s_ = dict.slots + ((u32)bsi_hash_key(ycw_[l0 + k]) & mask_);
-                        bsi_dict_head_cg(s_, f_[k], idx_[k], base_[k], lamd_[k]);
-#pragma unroll
-                        for (int i = 0; i < BSI_KW; ++i) st_[k][i] = bsi_ldcg_u64(&s_->st[i]);
-                    }
-#pragma unroll
-                    for (u32 k = 0; k < 8; ++k) {
-                        const u32 l = l0 + k;
-                        if (keep->lam[l] <= 1u) continue;
-                        bool hit = f_[k] == 2u;
-#pragma unroll
-                        for (int i = 0; i < BSI_KW; ++i) hit = hit && st_[k][i] == ycw_[l][i];
-                        // (not in its first slot: the full probe sequence)
-                        if (!hit) hit = bsi_dict_find(dict, ycw_[l], idx_[k], base_[k], lamd_[k]);
-                        if (hit && lamd_[k] == keep->lam[l]) {
-                            dbase_[l] = base_[k];
-                            dphase_[l] = idx_[k] - base_[k];
-                        } else {
-                            miss |= 1u << l;
-                        }
-                    }
-                }
-                use_dict = miss == 0u;
-            }
+        u32 pb_[BSI_N];
+        // (short cycles are walked: the key walk and the advance of a word take lam_max - 1 steps
+        //  each, which is cheaper than 32 lookups and two 32x32 transposes up to about 8 states)
+        if (dict.slots && lam_max > BSI_DICT_MIN_LAM) {
+            miss = bsi_dict_word(dict, ycw_, keep->lam, aux_s + tid, KEEP, keep->key, pb_);
+            use_dict = miss == 0u;
         }
         valid_out = valid;
         if (lam_max > 1u) { if (use_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) } }
         if (use_dict) {
-            // keys and P(c0) straight from the stored orbits: P(c0) = y advanced by adv steps
-            u64 cp_[32][BSI_KW];
-#pragma unroll 8
-            for (u32 l = 0; l < 32; ++l) {
-                const u32 lam = keep->lam[l];
-                if (lam > 1u) {
-                    u32 ph = dphase_[l] + aux_s[l * BSI_BLOCK + tid];
-                    if (ph >= lam) ph -= lam;
-                    const u64 *po = dict.orbit + (u64)(dbase_[l] + ph) * BSI_KW;
-                    const u64 *pk = dict.orbit + (u64)dbase_[l] * BSI_KW;
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) {
-                        cp_[l][i] = bsi_ldcg_u64(po + i);
-                        if (KEEP) keep->key[l][i] = bsi_ldcg_u64(pk + i);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) cp_[l][i] = lam ? ycw_[l][i] : 0ull;
-                }
-            }
-            BSI_PACK(b, cp_)
+            // keys and P(c0) came straight from the stored orbits
+            BSI_LOAD_MEM(b, pb_, 1)
         } else {
             // (throughput paths) the canonical keys, computed here: no separate pass over the records
             if (KEEP) {
@@ -1422,6 +1494,34 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                 bsi_warp_table_add(table, log2_slots, key0, have_uni ? uni_n : 0ull, uni_s1, uni_s2, 1u, ctr);
             }
         }
+        // acceptance of every lane first, each lane on its own (independent iterations: their local-
+        // and shared-memory loads overlap, where a loop over "the remaining lanes with this key" makes
+        // every load wait for the one before): ok = lanes whose attractor counts, tl_ = their
+        // trajectory lengths
+        u32 ok = 0u;
+        u64 tl_[32];
+#pragma unroll 4
+        for (u32 l = 0; l < 32; ++l) {
+            tl_[l] = 0ull;
+            if (!((todo >> l) & 1u)) continue;
+            const u64 mu = (u64)keep->c0[l] + (FROM_KEEP ? aux_s[l * BSI_BLOCK + threadIdx.x] : 0u);
+            const u64 lam = keep->lam[l];
+            if (mu + lam <= T) {                         // the loop stops at t = mu + lambda (model.py:201)
+                steps += BSI_LP_ORIGIN + mu + lam;
+                if (lam <= max_attractor_l) {            // attract.py:294
+                    tl_[l] = BSI_LP_ORIGIN + mu;         // trajectory_l, attract.py:298
+                    ok |= 1u << l;
+                } else {
+                    ++n_rej;
+                }
+            } else {                                     // closes only after max_t
+                steps += stop_t_cap;
+                ++n_rej;
+            }
+        }
+        n_acc += __popc(ok);
+        todo &= ok;                                      // rejected lanes add nothing to the table
+        // then one group per distinct key
         for (;;) {
             if (WARP_AGG ? !__any_sync(0xFFFFFFFFu, todo != 0u) : !todo) break;
             const u32 l0 = todo ? __ffs(todo) - 1 : 0u;
@@ -1430,31 +1530,25 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
             for (int i = 0; i < BSI_KW; ++i) key0[i] = todo ? keep->key[l0][i] : 0ull;
             const u32 lam0 = todo ? keep->lam[l0] : 0u;
             u64 n = 0, s1 = 0, s2 = 0;
-            u32 rest = todo;
-            while (rest) {
-                const u32 l = __ffs(rest) - 1;
-                rest &= rest - 1;
-                bool same = true;
+            if (todo) {
+                u32 grp = 0u;
+#pragma unroll 8
+                for (u32 l = 0; l < 32; ++l) {
+                    bool same = true;
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) same = same && (keep->key[l][i] == key0[i]);
-                if (!same) continue;
-                todo &= ~(1u << l);
-                const u64 mu = (u64)keep->c0[l] + (FROM_KEEP ? aux_s[l * BSI_BLOCK + threadIdx.x] : 0u);
-                const u64 lam = keep->lam[l];
-                if (mu + lam <= T) {                     // the loop stops at t = mu + lambda (model.py:201)
-                    steps += BSI_LP_ORIGIN + mu + lam;
-                    if (lam <= max_attractor_l) {        // attract.py:294
-                        const u64 tl = BSI_LP_ORIGIN + mu;   // trajectory_l, attract.py:298
-                        n += 1; s1 += tl; s2 += tl * tl;
-                    } else {
-                        ++n_rej;
-                    }
-                } else {                                 // closes only after max_t
-                    steps += stop_t_cap;
-                    ++n_rej;
+                    for (int i = 0; i < BSI_KW; ++i) same = same && (keep->key[l][i] == key0[i]);
+                    grp |= (same ? 1u : 0u) << l;
+                }
+                grp &= todo;
+                todo &= ~grp;
+                n = __popc(grp);
+#pragma unroll 8
+                for (u32 l = 0; l < 32; ++l) {
+                    const u64 tl = ((grp >> l) & 1u) ? tl_[l] : 0ull;
+                    s1 += tl;
+                    s2 += tl * tl;
                 }
             }
-            n_acc += n;
             if (WARP_AGG) {
                 __syncwarp();
                 bsi_warp_table_add(table, log2_slots, key0, n, s1, s2, lam0, ctr);
@@ -1498,6 +1592,45 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
+}
+
+// Orbits on request (reference attract.py:22-25: the states of an aggregated attractor, key state
+// first): thread i finds keys[i] in the cycle dictionary or stores its orbit there -- the same fast
+// walk the resolution kernels use (32 phases of the orbit per step) -- and reports where it starts
+// (bases[i]; ~0: not available, e.g. storage exhausted).  The host then copies the orbits out of the
+// dictionary's storage, and bsi_orbit_counts can count node activity there without a round trip.
+extern "C" __global__ void bsi_dict_learn_keys(const u64 *keys, const u64 *lams, u64 n, u64 *bases,
+                                               const BsiDict dict) {
+    // one 32-thread block per key: thread 0 claims and walks (the walk is one thread's work: its 32
+    // lanes are the parallelism), then the whole warp enters the states -- each entry is a couple of
+    // dependent L2 round trips, 32 of them in flight instead of one
+    const u64 i = blockIdx.x;
+    if (i >= n) return;
+    __shared__ u32 sh[3];
+    const u32 lam = lams[i] < 2ull || lams[i] > (u64)dict.cap_states ? 0u : (u32)lams[i];
+    if (threadIdx.x == 0u) {
+        bases[i] = ~0ull;
+        sh[0] = 0u;
+        if (lam) {
+            u64 key[BSI_KW];
+#pragma unroll
+            for (int k = 0; k < BSI_KW; ++k) key[k] = keys[i * BSI_KW + k];
+            u32 idx, base, lamd, slot;
+            if (bsi_dict_find(dict, key, idx, base, lamd)) {
+                if (idx == base && lamd == lam) bases[i] = base;
+            } else if (bsi_dict_claim(dict, key, lam, base, slot)) {
+                bsi_dict_store_orbit(dict, key, lam, base);
+                bases[i] = base;
+                sh[0] = 1u; sh[1] = base; sh[2] = slot;
+            }
+        }
+    }
+    __syncwarp();
+    if (sh[0]) {
+        bsi_dict_put_orbit(dict, lam, sh[1], threadIdx.x & 31u, 32u);
+        __syncwarp();
+        if (threadIdx.x == 0u) bsi_dict_publish(dict, sh[2]);
+    }
 }
 
 #endif  // BSI_UNIT != 5
@@ -1594,6 +1727,8 @@ bsi_resolve_finish(const BsiFound *found_q, const u64 *n_found_p, u64 few_words,
 #endif  // BSI_UNIT != 3, 6
 #endif  // BSI_UNIT 3, 5, 6
 
+#undef BSI_TRANSPOSE32
+#define BSI_TRANSPOSE32(A) bsi_transpose32(A)
 #if BSI_UNIT == 0 || BSI_UNIT == 4
 // ---- attractor table: export / merge ------------------------------------------------------------
 // Compacts the table into out[0 .. cap).  With `header` set, the last block to finish also writes
@@ -1774,6 +1909,7 @@ bsi_trajectories(u64 idx_begin, const u64 *indices, const u64 *codes, u64 n_lane
 extern "C" __global__ void bsi_orbit_counts(const u64 *states, const u64 *start, const u64 *lam, u64 *counts) {
     const u64 a = blockIdx.x;
     const u64 s0 = start[a], n = lam[a];
+    if (s0 == ~0ull) return;                      // (no orbit on the device for this one)
     for (u32 node = threadIdx.x; node < (u32)BSI_N; node += blockDim.x) {
         u64 c = 0;
         for (u64 t = 0; t < n; ++t) c += (states[(s0 + t) * BSI_KW + (node >> 6)] >> (node & 63u)) & 1ull;
@@ -1790,7 +1926,8 @@ extern "C" __global__ void bsi_orbit_counts(const u64 *states, const u64 *start,
 // x_T among x_lp .. x_{T-1} -- because after closure no new state, hence no hit, can appear
 // (model.py:201: the reference stops there); lanes neither hit nor closed go to the retry queue.
 // Lanes that end without a hit add their reference stop time to ctr->steps only in the final
-// round (stop time = max_t); closed lanes are reported in closed_q for exact stop-time accounting.
+// round (stop time = max_t); closed lanes are listed in closed_q and only COUNTED by the host (their
+// exact stop time, mu + lambda, is not worked out in this mode: see bsi_run_stats.steps).
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int check_closure,
                 u64 *hit_idx, u64 *hit_t, u64 hit_cap, u64 *retry_q, u64 *closed_q,

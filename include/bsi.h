@@ -131,7 +131,8 @@ typedef struct bsi_plan_opts {
                                   bsi_plan_op_counts) and skip NVRTC; the plan has no cubin */
     uint32_t keep_dict;        /* attract: 1 = bsi_attract_table_clear leaves the cycle dictionary as it is (it
                                   holds facts about the network's dynamics, not results) */
-    uint32_t reserved[3];
+    uint32_t tune;             /* experiment switches of the kernel template (BSI_TUNE), 0 = the shipped variant */
+    uint32_t reserved[2];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */
@@ -148,8 +149,10 @@ typedef struct bsi_run_stats {
     uint64_t n_found;          /* attract: problems whose attractor passed both caps; target: hits */
     uint64_t n_without;        /* attract: problems with no attractor within the caps */
     uint64_t steps;            /* sum over problems of the reference's stop time (model.py:235);
-                                  target mode: exact for hits, max_t for the others (an upper bound
-                                  when a trajectory closes its cycle before max_t without a hit) */
+                                  target mode: exact for hits; a problem without a hit counts max_t
+                                  (an upper bound when its trajectory closes its cycle earlier) when
+                                  max_t is finite and NOTHING when max_t = BSI_INF (it stops at its
+                                  cycle closure, a time this mode does not work out) */
     uint64_t device_steps;     /* 32-lane word-steps actually executed by the main kernels */
     uint64_t launches;         /* kernels launched by this call */
     uint64_t rounds;           /* attract / target: detection rounds over all chunks */
@@ -170,8 +173,9 @@ int bsi_device_count(int *count);
 int bsi_release_cached_memory(void);
 
 /* ---- plan: network + problem space + mode, specialised through NVRTC for one device ------- */
-/* Compiled kernels are cached per process.  Environment BSI_CACHE_DIR=<directory> (off when unset)
- * adds an on-disk level, so that later processes skip the few seconds of NVRTC per network. */
+/* Compiled kernels are cached per process and, so that later processes skip the few seconds of NVRTC
+ * per network, on disk: in $BSI_CACHE_DIR if set ("" or "off" disable the disk level), else in
+ * $XDG_CACHE_HOME/boolsi_b200, else in ~/.cache/boolsi_b200. */
 /* Replaces the per-run set-up of the reference: configure_solve_simulation_problem
  * (mpi.py:351-376: the mode's per-trajectory function with its caps bound), the fixed-node
  * rewrite of the rules (model.py:31-49, re-done per batch at mpi.py:525-528) and the numeral
@@ -193,6 +197,13 @@ int bsi_plan_key_words(const bsi_plan *plan, uint32_t *kw);
 /* A plan starts on its own non-blocking stream.  cuda_stream: a cudaStream_t / CUstream handle;
  * NULL = the CUDA default (legacy) stream; (void *)-1 = back to the plan's own stream. */
 int bsi_plan_set_stream(bsi_plan *plan, void *cuda_stream);
+/* Progress of long runs (replaces the reference's TickingProgressBar feed, utils.py:19-54, mpi.py:164):
+ * `fn(done, total, user)` is called from the run functions after every finished wave of problems
+ * (2^chunk_log2 of them; the host has waited for a wave when the run needs several detection rounds,
+ * i.e. always when max_t has no cap) -- from the calling thread for a plan, from the member's host
+ * thread for a group.  NULL switches it off.  The callback must not call back into the plan. */
+typedef void (*bsi_progress_fn)(uint64_t done, uint64_t total, void *user);
+int bsi_plan_set_progress(bsi_plan *plan, bsi_progress_fn fn, void *user);
 /* Generated CUDA source / build log (NUL-terminated, owned by the plan; diagnostics, no reference
  * counterpart). */
 const char *bsi_plan_source(const bsi_plan *plan);
@@ -258,6 +269,14 @@ int bsi_attractor_states(bsi_plan *plan, const uint64_t *key, uint64_t lambda, u
 int bsi_attractor_states_batch(bsi_plan *plan, const uint64_t *keys, uint64_t n, uint64_t n_states,
                                uint64_t *out);
 
+/* Orbits of `n` attractors, each exactly its own length: keys[n][key_words], lams[n] in; `states` out,
+ * orbit i at state offset lams[0] + .. + lams[i-1], key state first (the rotation of attract.py:22-25).
+ * Orbits the run stored in its cycle dictionary are copied from there; the others are entered into it
+ * first (one fast walk per attractor).  With `counts` != NULL also their node activity
+ * (counts[n][n_nodes], see bsi_attractor_activity), counted on the device where the orbits lie, in the
+ * same pass.  HOST buffers. */
+int bsi_attractor_orbits(bsi_plan *plan, const uint64_t *keys, const uint64_t *lams, uint64_t n,
+                         uint64_t *states, uint64_t *counts);
 /* Node activity of attractors (attractor_analysis.py:49-51: each attractor as an observation in [0,1]^N):
  * counts[i][node] = number of states of attractor i's cycle in which `node` is on (its mean activity is
  * counts / lambda).  Counted on the device from the orbits -- the ones the run stored, else regenerated.

@@ -9,6 +9,10 @@ for p in (REPO, os.path.join(REPO, 'tests'), os.path.join(REPO, 'tests', 'golden
         sys.path.insert(0, p)
 
 
+# the tests stay inside the repo: no kernel cache in the user's home (the disk-cache test names its own)
+os.environ.setdefault('BSI_CACHE_DIR', 'off')
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 

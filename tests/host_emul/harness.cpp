@@ -36,6 +36,7 @@ static inline u32 bsi_lop3(u32 a, u32 b, u32 c) {
 }
 
 // the contract of the device function (B[r] bit c = A[31-c] bit 31-r), bit by bit
+#define BSI_TRANSPOSE32(A) bsi_transpose32(A)
 static void bsi_transpose32(unsigned int (&A)[32]) {
     unsigned int B[32];
     for (int r = 0; r < 32; ++r) {

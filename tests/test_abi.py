@@ -75,7 +75,8 @@ def test_no_gpu_is_an_error_not_a_fallback(built):
 
 
 def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
-    """BSI_CACHE_DIR (off by default): the first process compiles and stores one file per unit,
+    """The disk level of the kernel cache (BSI_CACHE_DIR; by default the user's cache directory, "off"
+    disables it): the first process compiles and stores one file per unit,
     the second one loads them instead of running NVRTC and gets byte-identical kernels; a
     damaged file is ignored (recompiled), never trusted."""
     import hashlib
@@ -96,9 +97,7 @@ def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
 
     def run(cache_dir):
         env = dict(os.environ)
-        env.pop('BSI_CACHE_DIR', None)
-        if cache_dir is not None:
-            env['BSI_CACHE_DIR'] = str(cache_dir)
+        env['BSI_CACHE_DIR'] = 'off' if cache_dir is None else str(cache_dir)
         out = subprocess.run([sys.executable, '-c', script], env=env, capture_output=True, text=True, check=True)
         seconds, digest, size = out.stdout.split()
         return float(seconds), digest, int(size)
@@ -117,4 +116,4 @@ def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
     again = run(tmp_path)
     assert again[1:] == cold[1:]
     assert open(victim, 'rb').read() == data                      # rewritten after the recompile
-    assert run(None)[1:] == cold[1:]                              # and without the variable: plain NVRTC
+    assert run(None)[1:] == cold[1:]                              # and with the disk level off: plain NVRTC

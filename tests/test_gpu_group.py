@@ -169,3 +169,19 @@ def test_node_activity_counts_on_the_device(opts):
         a.node_on_counts = None
     obs2, freq2 = analysis.node_activity(attractors)          # the reference's way: mean over the states
     assert np.array_equal(obs, obs2) and np.array_equal(freq, freq2)
+
+
+def test_progress_callback_reports_finished_waves():
+    """bsi_plan_set_progress: one call per finished wave of problems (chunk_log2), monotone, ending at
+    the total -- the feed of the reference's progress bar (utils.py:19-54)."""
+    args, pk = _attract_problem(64, 2, 1, 14)
+    seen = []
+    with _lib.Group(pk, _lib.MODE_ATTRACT, devices=[0], chunk_log2=11) as group:
+        group.set_progress(lambda member, done, total: seen.append((member, done, total)))
+        group.attract_run(0, pk.n_problems, inf, inf)
+        group.set_progress(None)
+        n_calls = len(seen)
+        group.attract_run(0, pk.n_problems, inf, inf)
+    assert n_calls == len(seen) == 8                      # 2^14 problems in waves of 2^11; none after switching off
+    assert [d for _, d, _ in seen] == [2048 * (i + 1) for i in range(8)]
+    assert all(m == 0 and t == pk.n_problems for m, _, t in seen)
