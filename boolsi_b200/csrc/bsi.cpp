@@ -123,6 +123,9 @@ struct Counters {
 };
 constexpr size_t kPerRoundBytes = 7 * sizeof(uint64_t);
 constexpr int kMaxCk = 72;
+// (bsi_template.cuh: BSI_SCRATCH_WORDS, BSI_EQ_ENTRY_BYTES)
+constexpr size_t kScratchWords = 160;
+constexpr size_t early_entry_bytes(int n_nodes) { return 8 + 4 + 4 + 32 * 4 + 32 * 4 + 4 * (size_t)n_nodes; }
 struct Sched {
     uint32_t n_ck, end, first_final, pad;
     uint32_t ck_time[kMaxCk];
@@ -209,7 +212,7 @@ struct bsi_plan {
                f_export = nullptr, f_merge = nullptr, f_merge_payloads = nullptr, f_traj = nullptr, f_counts = nullptr, f_learn_keys = nullptr,
                f_target = nullptr;
     int n_sms = 0;
-    int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0;
+    int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0, early_blocks_per_sm = 0;
     size_t main_smem = 0;
     int smem_slots = 3;
     uint32_t table_log2 = 20;
@@ -673,6 +676,8 @@ int load_plan(bsi_plan *p, int device) {
         p->key_blocks_per_sm = std::max(1, std::min(a, 8));
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_mu, p->block, 0));
         p->mu_blocks_per_sm = std::max(1, a);
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_early, p->block, 0));
+        p->early_blocks_per_sm = std::max(1, a);
         p->table_log2 = p->opts.table_log2_slots ? p->opts.table_log2_slots : 20;
         if (p->table_log2 < 4 || p->table_log2 > 28) return fail(BSI_E_ARG, "table_log2_slots out of range");
         const size_t slot_bytes = (size_t)8 * p->m.kw + 32;
@@ -958,8 +963,8 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
     const uint64_t chunk = (uint64_t)1 << chunk_log2;
     const size_t found_bytes = 24 + 24 * (size_t)p->m.kw;
     const unsigned main_grid = (unsigned)(p->n_sms * p->main_blocks_per_sm);
-    // per thread: detection records (3 x 32 words) + the checkpoint slots that are not in shared memory
-    const size_t scratch_bytes = (size_t)main_grid * p->block * (96 + (size_t)(3 - p->smem_slots) * p->m.n) * sizeof(uint32_t);
+    // per thread: detection records (3 x 32 words), early events (2 x 32 words) + the checkpoint slots that are not in shared memory
+    const size_t scratch_bytes = (size_t)main_grid * p->block * (kScratchWords + (size_t)(3 - p->smem_slots) * p->m.n) * sizeof(uint32_t);
     if ((rc = ensure(p, p->scratch, scratch_bytes))) return rc;
 
     CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
@@ -997,7 +1002,7 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                 // early-word queue: one entry per word at most
                 uint64_t early_cap = p->opts.no_early_words ? 0 : n_words;
                 if (early_cap &&
-                    (rc = ensure(p, p->early_q, ((early_cap + 31) / 32) * 32 * (8 + 4 + 32 * 8 + 4 * (size_t)p->m.n))))   // whole blocks of 32 entries
+                    (rc = ensure(p, p->early_q, ((early_cap + 31) / 32) * 32 * early_entry_bytes(p->m.n))))   // whole blocks of 32 entries
                     return rc;
                 CUdeviceptr early_p = early_cap ? p->early_q.p : 0;
                 void *args[] = {&word0, &n_words, &b, &e, &sched, (void *)&final_round, &stop_t,
@@ -1034,7 +1039,7 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                     CUdeviceptr n_early_p = p->ctr.p + offsetof(Counters, n_early);
                     void *args_e[] = {&early_p, &early_cap, &n_early_p, &n_found_p, &few, &t_rel, &cap_l,
                                       &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};
-                    if ((rc = launch(p, p->f_early, grid_m, p->block, 0, args_e))) return rc;
+                    if ((rc = launch(p, p->f_early, (unsigned)(p->n_sms * p->early_blocks_per_sm), p->block, 0, args_e))) return rc;
                 }
                 void *args_r[] = {&p->found_q.p, &n_found_p, &few, &early_p, &early_cap, &t_rel, &cap_l,
                                   &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};

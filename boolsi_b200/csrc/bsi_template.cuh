@@ -118,23 +118,31 @@ struct BsiFound {       // one lane that matched a checkpoint
 };
 
 // Early-word queue (dense rounds only): a word whose lanes matched EARLY checkpoints hands them
-// over bit-sliced -- no per-lane records, no transposes.  Entries come in blocks of 32 (the 32
-// threads of a warp reserve consecutive entries and later read consecutive entries), and a block
-// is one contiguous piece of memory, structure of arrays inside:
-//   u64 word[32]; u64 lamc[32 lanes][32] (lambda | c << 32); u32 mask[32]; u32 y[N][32] (the latch)
-// so that a warp's ~100 loads per entry hit a few adjacent DRAM pages instead of 100 planes that
-// lie `cap` entries apart (measured: the plane layout kept the resolution kernel waiting on
-// memory for a third of its time).
-#define BSI_EQ_BLOCK_BYTES (32ull * (8ull + 32ull * 8ull + 4ull + 4ull * BSI_N))
+// over bit-sliced -- no per-lane records, no transposes.  What it hands over is the word's state at
+// the time j_end its loop ended: every matched lane has stayed on its cycle since it matched, so
+// that ONE state (all lanes at the same time) is an on-cycle state of each of them -- no latch of the
+// matched checkpoints is needed -- plus the list of its match EVENTS (lanes, lambda): lanes that
+// matched the same checkpoint at the same time share their cycle length, so a word of 32 lanes has
+// a handful of events and the resolution works per event, not per lane.  Entries come in blocks of
+// 32 (the 32 threads of a warp reserve consecutive entries and later read consecutive entries), and a
+// block is one contiguous piece of memory, structure of arrays inside:
+//   u64 word[32]; u32 mask[32]; u32 info[32] (n_events | j_end << 8); u32 evm[32 events][32];
+//   u32 evl[32 events][32]; u32 y[N][32]
+// so that a warp's loads per entry hit a few adjacent DRAM pages instead of planes that lie `cap`
+// entries apart.
+#define BSI_EQ_ENTRY_BYTES (8ull + 4ull + 4ull + 32ull * 4ull + 32ull * 4ull + 4ull * BSI_N)
+#define BSI_EQ_BLOCK_BYTES (32ull * BSI_EQ_ENTRY_BYTES)
 struct BsiEarlyQ {
     unsigned char *base;
     u64 cap;
 };
 struct BsiEarlyEntry {
     u64 *word;          // [0]
-    u64 *lamc;          // [lane * 32]
-    u32 *mask;          // [0]
-    u32 *y;             // [node * 32]
+    u32 *mask;          // [0]  the lanes handed over
+    u32 *info;          // [0]  n_events | j_end << 8
+    u32 *evm;           // [event * 32]  lanes of the event
+    u32 *evl;           // [event * 32]  their cycle length
+    u32 *y;             // [node * 32]   x at time j_end
 };
 __device__ __forceinline__ BsiEarlyQ bsi_early_view(void *base, u64 cap) {
     BsiEarlyQ q;
@@ -147,9 +155,11 @@ __device__ __forceinline__ BsiEarlyEntry bsi_early_entry(const BsiEarlyQ &q, u64
     const u32 k = (u32)e & 31u;
     BsiEarlyEntry r;
     r.word = (u64 *)blk + k;
-    r.lamc = (u64 *)blk + 32 + k;
-    r.mask = (u32 *)(blk + 33ull * 32ull * 8ull) + k;
-    r.y = r.mask + 32;
+    r.mask = (u32 *)(blk + 32ull * 8ull) + k;
+    r.info = r.mask + 32;
+    r.evm = r.info + 32;
+    r.evl = r.evm + 32 * 32;
+    r.y = r.evl + 32 * 32;
     return r;
 }
 
@@ -175,6 +185,7 @@ struct BsiRec {         // == bsi_attractor_rec (include/bsi.h)
 #define BSI_ZERO_A(i) a##i = 0u;
 #define BSI_COPY_AB(i) a##i = b##i;
 #define BSI_COPY_CA(i) c##i = a##i;
+#define BSI_COPY_CB_(i) c##i = b##i;
 #define BSI_SAVE_K0(i) k0_##i = a##i;
 #define BSI_SAVE_K1(i) k1_##i = a##i;
 #define BSI_SAVE_K2(i) k2_##i = a##i;
@@ -506,8 +517,10 @@ __device__ __forceinline__ void bsi_warp_table_add(BsiSlot *table, u32 log2_slot
 // dynamic shared memory of the main kernel: the three checkpoint slots in full,
 // u32 ck[3][N][BLOCK] (48 KB per 64-thread block at N = 64; four blocks per SM fit).  The
 // per-thread scratch in global memory (sized by the persistent grid) only holds the detection
-// records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32] (the matched states
-// themselves stay in shared memory / in a bit-sliced latch until the end of the word).
+// records of the thread's 32 lanes: u32 lam[32], u32 c[32], u32 c0[32] for matches against final
+// checkpoints (the matched states themselves stay in shared memory until the end of the word) and
+// the event list of the early matches, u32 evm[32], u32 evl[32] (BSI_SCRATCH_WORDS in all).
+#define BSI_SCRATCH_WORDS 160ull
 #ifdef BSI_HOST_EMUL
 extern unsigned char bsi_smem[];
 #else
@@ -529,28 +542,20 @@ __device__ __forceinline__ u32 bsi_slow_match(const u32 *xs, const u32 *ck, u64 
 // (= the checkpoint itself) and the previous checkpoint are extracted from shared memory at the end
 // of the word, when all threads of the warp do so together instead of one diverged thread now.
 #define BSI_DEFERRED 0x80000000u
-// A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten) is
-// only noted as well: the matched state IS the checkpoint's, so the matched lanes stay `pending`
-// and their bits are copied from slot 0 into the bit-sliced latch yl right before that slot is
-// overwritten (and at the end of the word) -- one pass over the nodes per CHECKPOINT that had
-// matches, not per match event (a word of the regime where every lane closes after a transient of
-// its own has up to 32 events but matches against a handful of checkpoints).  The per-lane state
-// codes come out of one 32x32-transpose pass at the end of the word.
-__device__ __forceinline__ void bsi_record(u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s, u64 sstride, u32 slot,
-                                           bool deferred) {
+// A match against an EARLY checkpoint (slot 0 before its final time; it will be overwritten) is one
+// EVENT: its lanes and their common cycle length, two words, whatever the number of lanes.  Nothing
+// of the matched state is kept: the lanes go on being updated with the rest of the word, so the
+// word's state when its loop ends is an on-cycle state of every one of them (see the early-word
+// queue above).  A word has at most 32 events (every event retires at least one lane).
+__device__ __forceinline__ void bsi_record(u32 m, u32 lam, u32 c, u32 *lam_s, u32 *c_s, u64 sstride, u32 slot) {
     u32 *c0_s = c_s + 32ull * sstride;
     while (m) {
         const u32 l = __ffs(m) - 1;
         m &= m - 1;
         lam_s[l * sstride] = lam;
         c_s[l * sstride] = c;
-        c0_s[l * sstride] = deferred ? (BSI_DEFERRED | slot) : 0u;
+        c0_s[l * sstride] = BSI_DEFERRED | slot;
     }
-}
-// yl <- slot 0's checkpoint in the lanes of m
-__device__ __forceinline__ void bsi_latch_pending(u32 *yl, const u32 *ck0, u64 cstride, u32 m) {
-#pragma unroll 8
-    for (int i = 0; i < BSI_N; ++i) yl[i] = (yl[i] & ~m) | (ck0[i * cstride] & m);
 }
 
 // DENSE: words of the contiguous index range [idx_begin, idx_end), word0 = idx_begin >> 5.
@@ -570,7 +575,9 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
     u32 *const c_s = lam_s + 32ull * sstride;                         // [32][sstride], then c0 [32]
     // checkpoint slot S: the first BSI_SMEM_SLOTS slots live in shared memory, the later ones
     // (armed for the shortest time) in this thread's scratch, [slot][node][sstride], L2-resident
-    u32 *const ck_g = scratch + 96ull * sstride + gtid;
+    u32 *const evm_s = scratch + 96ull * sstride + gtid;              // [32][sstride] early events: lanes
+    u32 *const evl_s = evm_s + 32ull * sstride;                       // [32][sstride]               lambda
+    u32 *const ck_g = scratch + BSI_SCRATCH_WORDS * sstride + gtid;
     (void)ck_g;
 #define BSI_CK_ONCHIP(S) (BSI_SMEM_SLOTS == 3 || (S) < BSI_SMEM_SLOTS)
 #define BSI_CK_PTR(S) (BSI_CK_ONCHIP(S) ? ck_s + (S) * BSI_N * BSI_BLOCK \
@@ -588,9 +595,8 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         BSI_FOR_FILTER(BSI_DECL_K1)
         BSI_FOR_FILTER(BSI_DECL_K2)
         u32 valid = 0u, F = 0u, alive = 0u, early = 0u;
-        u32 pend = 0u;                           // early-matched lanes whose state is still only in slot 0
+        u32 n_ev = 0u, j_end = 0u;               // early events so far; the time the loop ended at
         u32 st0 = 0, st1 = 0, st2 = 0;           // checkpoint time held by each slot
-        u32 yl_[BSI_N];                          // bit-sliced latch of the early matches' states
 
         if (active) {
             // ---- x_0 .. x_lp ----------------------------------------------------------------
@@ -635,13 +641,21 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         if (cand_) {                                                                 \
             BSI_COUNT(1)                                                             \
             u32 m_ = bsi_slow_match(XS, BSI_CK_PTR(S), BSI_CK_STRIDE(S), cand_);       \
-            if (m_) {                                                                \
-                F |= m_;                                                             \
-                alive &= ~m_;                                                        \
-                bsi_record(m_, (J) - (ST), (ST), lam_s, c_s, sstride, (S),           \
-                           (S) > 0 || (ST) >= sched.first_final);                    \
-                if (!((S) > 0 || (ST) >= sched.first_final)) { early |= m_; pend |= m_; } \
-            }                                                                        \
+            if (m_) { BSI_MATCHED(m_, J, S, ST) }                                    \
+        }                                                                            \
+    }
+            // lanes M matched the checkpoint of slot S (taken at time ST) at time J
+#define BSI_MATCHED(M, J, S, ST)                                                     \
+    {                                                                                \
+        F |= (M);                                                                    \
+        alive &= ~(M);                                                               \
+        if ((S) > 0 || (ST) >= sched.first_final) {                                  \
+            bsi_record((M), (J) - (ST), (ST), lam_s, c_s, sstride, (S));             \
+        } else {                                                                     \
+            early |= (M);                                                            \
+            evm_s[n_ev * sstride] = (M);                                             \
+            evl_s[n_ev * sstride] = (J) - (ST);                                      \
+            ++n_ev;                                                                  \
         }                                                                            \
     }
 #if BSI_STATS
@@ -691,13 +705,7 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
             u32 acc_ = p0 | ~alive;                                                  \
             BSI_CMP_ALL_MEM(acc_, X, BSI_CK_PTR(0), BSI_CK_STRIDE(0))                \
             const u32 m_ = ~acc_;                                                    \
-            if (m_) {                                                                \
-                const bool def_ = st0 >= sched.first_final;                          \
-                F |= m_;                                                             \
-                alive &= ~m_;                                                        \
-                bsi_record(m_, (J) - st0, st0, lam_s, c_s, sstride, 0u, def_);       \
-                if (!def_) { early |= m_; pend |= m_; }                              \
-            }                                                                        \
+            if (m_) { BSI_MATCHED(m_, J, 0u, st0) }                                  \
         }                                                                            \
     }
 #define BSI_SLOW2(X, J)                                                              \
@@ -764,10 +772,6 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                 // checkpoint due at time j: state a (already compared) goes into its slot
                 if (ci < sched.n_ck && sched.ck_time[ci] == j) {
                     const u32 s = sched.ck_slot[ci];
-                    if (s == 0u && pend) {
-                        bsi_latch_pending(yl_, BSI_CK_PTR(0), BSI_CK_STRIDE(0), pend);
-                        pend = 0u;
-                    }
                     if (BSI_CK_ONCHIP(s)) {
                         u32 *p_ = ck_s + s * BSI_N * BSI_BLOCK;
                         BSI_STORE_ALL(a, p_, BSI_BLOCK)
@@ -793,29 +797,29 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
 #undef BSI_SEGMENT
 #undef BSI_FULL
 #undef BSI_STAGE2
+#undef BSI_MATCHED
+            j_end = j;
         }
 
         // ---- results ------------------------------------------------------------------------------
-        if (pend) {
-            bsi_latch_pending(yl_, BSI_CK_PTR(0), BSI_CK_STRIDE(0), pend);
-            pend = 0u;
-        }
         const u32 matched = F;
-        // early matches of a dense word -> early-word queue, bit-sliced as they are
+        // early matches of a dense word -> early-word queue: the word's state now (time j_end) and
+        // the event list
         if (DENSE && early_cap) {
             const u64 e = bsi_reserve(&ctr->n_early, early ? 1u : 0u);
             if (early) {
                 const BsiEarlyEntry q = bsi_early_entry(bsi_early_view(early_base, early_cap), e);
                 q.word[0] = word0 + w;
                 q.mask[0] = early;
-                // (unrolled with predication, not a loop over the set bits: the record loads are
-                // L2 round trips, and a word of the ordered regime has all 32 lanes here)
+                q.info[0] = n_ev | (j_end << 8);
+                // (unrolled with predication: the event loads are L2 round trips, in flight together)
 #pragma unroll 8
-                for (u32 l = 0; l < 32; ++l)
-                    if ((early >> l) & 1u)
-                        q.lamc[l * 32u] = (u64)lam_s[l * sstride] | ((u64)c_s[l * sstride] << 32);
-#pragma unroll 8
-                for (int i = 0; i < BSI_N; ++i) q.y[i * 32] = yl_[i];
+                for (u32 k = 0; k < 32; ++k)
+                    if (k < n_ev) {
+                        q.evm[k * 32u] = evm_s[k * sstride];
+                        q.evl[k * 32u] = evl_s[k * sstride];
+                    }
+                BSI_STORE_ALL(a, q.y, 32)
                 F &= ~early;
                 early = 0u;
             }
@@ -826,13 +830,24 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
         const u32 n_u = __popc(U);
         u64 base_f = bsi_reserve(&ctr->n_found, n_f);
         if (n_f) {
-            // state codes of the early matches: one transpose pass over the latch
+            // early matches without an early-word queue (retry rounds): per-lane records with the
+            // lane's state now as the on-cycle state (y = x_c with c = j_end >= mu, c0 = 0) -- one
+            // transpose pass over the word's state for the state codes
             u64 cw_[32][BSI_KW];
             if (early) {
-#define BSI_LOAD_YL(i) a##i = yl_[i];
-                BSI_FOR_NODES(BSI_LOAD_YL)
-#undef BSI_LOAD_YL
                 BSI_UNPACK(cw_, a)
+#pragma unroll 1
+                for (u32 k = 0; k < n_ev; ++k) {
+                    u32 m = evm_s[k * sstride];
+                    const u32 lam = evl_s[k * sstride];
+                    while (m) {
+                        const u32 l = __ffs(m) - 1;
+                        m &= m - 1;
+                        lam_s[l * sstride] = lam;
+                        c_s[l * sstride] = j_end;
+                        c_s[(32 + l) * sstride] = 0u;
+                    }
+                }
             }
             u32 m = F;
             while (m) {
@@ -1079,20 +1094,19 @@ __device__ __forceinline__ void bsi_key_word(BsiFound *found_q, u64 n_found, u64
 // The dictionary's part of resolving one word, OUT OF LINE (the resolution kernels are big; what a
 // word of short cycles never executes must not sit in the instruction cache's way): look the matched
 // states ycw[l] of the lanes on cycles up -- eight independent probes in flight at a time -- and, if
-// the dictionary knows them ALL, fetch P(c0) = y advanced by adv[l] steps (pcode) and, with
+// the dictionary knows them ALL, fetch P(c0) = y advanced by adv_s[l * adv_stride] steps and, with
 // want_keys, the canonical keys (keys[l]) from the stored orbits; pb receives P(c0) bit-sliced, one
-// word per node.  Returns the lanes it does not know (0: pb / keys are filled).
+// word per node, dbase_[l] where the lane's orbit is stored (one number per attractor).  Returns
+// the lanes it does not know (0: pb / keys / dbase_ are filled).
 struct BsiKeep {        // what bsi_finish_word needs of the 32 records, when it runs in the same kernel
     u64 key[32][BSI_KW];
     u32 lam[32], c0[32];
-    // early words only: all valid lanes are fixed points (lambda = 1, c0 = 0) holding the SAME
-    // state -- the ordered regime's normal case.  Then only key[first valid lane] is filled.
-    u32 uniform;
 };
 __device__ __noinline__ u32 bsi_dict_word(const BsiDict &dict, u64 (*ycw)[BSI_KW], const u32 *lam, const u32 *adv_s,
-                                          bool want_keys, u64 (*keys)[BSI_KW], u32 *pb) {
+                                          u32 adv_stride, bool want_keys, u64 (*keys)[BSI_KW], u32 *pb,
+                                          u32 *dbase_) {
     const u32 mask_ = (1u << dict.log2_slots) - 1u;
-    u32 dbase_[32], dphase_[32];
+    u32 dphase_[32];
     u32 miss = 0u;
 #pragma unroll 1
     for (u32 l0 = 0; l0 < 32; l0 += 8) {
@@ -1131,7 +1145,7 @@ __device__ __noinline__ u32 bsi_dict_word(const BsiDict &dict, u64 (*ycw)[BSI_KW
             const u32 l = l0 + k;
             const u32 lm = lam[l];
             if (lm > 1u) {
-                u32 ph = dphase_[l] + adv_s[l * BSI_BLOCK];
+                u32 ph = dphase_[l] + adv_s[l * adv_stride];
                 if (ph >= lm) ph -= lm;
                 const u64 *po = dict.orbit + (u64)(dbase_[l] + ph) * BSI_KW;
                 const u64 *pk = dict.orbit + (u64)dbase_[l] * BSI_KW;
@@ -1163,14 +1177,13 @@ __device__ __noinline__ u32 bsi_dict_word(const BsiDict &dict, u64 (*ycw)[BSI_KW
 // a* walks x_j from x_c0 (the shipped checkpoint state, or the problem index when c0 = 0), b*
 // walks P(j); three register sets rotate so that no step needs a copy.
 // Reference attract.py:287-300 (mu, trajectory_l), attract.py:374-402 (aggregate).
-// EARLY: the lanes are those of early-word queue entry w (their states bit-sliced in its y field, all
-// starting from the dense problem-index word in its word field, c0 = 0); otherwise word w of found_q.
+// The lanes are those of word w of found_q.
 // `keep` always receives lambda and c0 of the lanes; with KEEP also their canonical keys (from the
 // cycle dictionary when it knows every cycle of the word, else by the walk of bsi_key_core -- the
 // walked cycles are then entered into the dictionary).
-template <bool WRITE_PAD, bool KEEP, bool EARLY>
+template <bool WRITE_PAD, bool KEEP>
 __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 w, u32 *aux_s,
-                                            BsiCounters *ctr, BsiKeep *keep, const BsiEarlyQ &eq,
+                                            BsiCounters *ctr, BsiKeep *keep,
                                             const BsiDict &dict, bool learn, u32 &valid_out) {
     const u32 tid = threadIdx.x;
     {
@@ -1178,37 +1191,11 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
         u32 valid = 0u, adv_max = 0u, c_max = 0u, from_idx = 0u, lam_max = 0u;
-        const BsiEarlyEntry ent = bsi_early_entry(eq, EARLY ? w : 0ull);
-        (void)ent;
         // one pass over the 32 records of this word: every field that is needed later goes to
         // (thread-interleaved, hence coalesced) local arrays
-        u64 cw_[EARLY ? 1 : 32][BSI_KW], cz_[EARLY ? 1 : 32][BSI_KW], cx_[EARLY ? 1 : 32][BSI_KW];
-        if (EARLY) {
-            valid = ent.mask[0];
-            from_idx = valid;
-            // all 32 queue loads first (independent, in flight together; ncu: one exposed DRAM
-            // latency per lane was a third of this kernel), then the per-lane work
-            u64 lc_[32];
-#pragma unroll
-            for (u32 l = 0; l < 32; ++l) lc_[l] = ((valid >> l) & 1u) ? ent.lamc[l * 32u] : 1ull;
+        u64 cw_[32][BSI_KW], cz_[32][BSI_KW], cx_[32][BSI_KW];
 #pragma unroll 1
-            for (u32 l = 0; l < 32; ++l) {
-                keep->lam[l] = 0u;
-                if (!((valid >> l) & 1u)) continue;
-                const u64 lc = lc_[l];
-                const u32 lam = (u32)lc, c = (u32)(lc >> 32);
-                // (fixed points, the bulk of the ordered regime, need no division)
-                const u32 adv = lam == 1u ? 0u : (lam - c % lam) % lam;
-                aux_s[l * BSI_BLOCK + tid] = adv;
-                adv_max = max(adv_max, adv);
-                c_max = max(c_max, c);
-                lam_max = max(lam_max, lam);
-                keep->lam[l] = lam;
-                keep->c0[l] = 0u;
-            }
-        }
-#pragma unroll 1
-        for (u32 l = 0; !EARLY && l < 32; ++l) {
+        for (u32 l = 0; l < 32; ++l) {
             const u64 q = BSI_Q(w, l);
             u64 x_[BSI_KW];
 #pragma unroll
@@ -1243,44 +1230,16 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #pragma unroll
             for (int i = 0; i < BSI_KW; ++i) cx_[l][i] = x_[i];
         }
-        bool uniform = false;
-        if (!EARLY) keep->uniform = 0u;
-        if (EARLY) {
-            BSI_LOAD_MEM(b, ent.y, 32)
-            if (lam_max <= 1u && valid) {
-                // all fixed points: do the valid lanes hold one and the same state?  (two ops per
-                // node instead of the 32x32 transposes and the per-lane key compares)
-                const u32 l0_ = __ffs(valid) - 1;
-                u32 diff_ = 0u;
-                u64 ukey_[BSI_KW];
-#pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) ukey_[i] = 0ull;
-#define BSI_UNI_NODE(i)                                                           \
-    {                                                                             \
-        const u32 r_ = 0u - ((b##i >> l0_) & 1u);                                 \
-        diff_ |= (b##i ^ r_) & valid;                                             \
-        ukey_[(i) >> 6] |= (u64)(r_ & 1u) << ((i) & 63);                          \
-    }
-                BSI_FOR_NODES(BSI_UNI_NODE)
-#undef BSI_UNI_NODE
-                uniform = diff_ == 0u;
-                if (uniform) {
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) keep->key[l0_][i] = ukey_[i];
-                }
-            }
-            if (!uniform) BSI_UNPACK(keep->key, b)   // the states as codes: keys of the fixed points
-            keep->uniform = uniform ? 1u : 0u;
-        }
         // ---- lanes on cycles (lambda > 1): does the dictionary know every one of them? -----------
-        u64 (*const ycw_)[BSI_KW] = EARLY ? keep->key : cw_;      // the matched states as codes
+        u64 (*const ycw_)[BSI_KW] = cw_;                          // the matched states as codes
         u32 miss = 0u;
         bool use_dict = false;
         u32 pb_[BSI_N];
         // (short cycles are walked: the key walk and the advance of a word take lam_max - 1 steps
         //  each, which is cheaper than 32 lookups and two 32x32 transposes up to about 8 states)
         if (dict.slots && lam_max > BSI_DICT_MIN_LAM) {
-            miss = bsi_dict_word(dict, ycw_, keep->lam, aux_s + tid, KEEP, keep->key, pb_);
+            u32 dbase_[32];
+            miss = bsi_dict_word(dict, ycw_, keep->lam, aux_s + tid, BSI_BLOCK, KEEP, keep->key, pb_, dbase_);
             use_dict = miss == 0u;
         }
         valid_out = valid;
@@ -1302,11 +1261,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
                     }
                 }
             }
-            if (EARLY) {
-                if (!uniform) BSI_LOAD_MEM(b, ent.y, 32)      // (again: the transposes took the registers)
-            } else {
-                BSI_PACK(b, cw_)
-            }
+            BSI_PACK(b, cw_)
             // ---- b <- P(c0): advance each lane by its own number of steps ---------------------
 #define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
             {
@@ -1336,21 +1291,15 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
 #define BSI_MASK_A(i) a##i &= from_idx;
 #define BSI_OR_AB(i) a##i |= b##i;
             BSI_FOR_NODES(BSI_COPY_CB)
-            if (EARLY) {
-                const u64 W_ = ent.word[0];
-                BSI_INIT_DENSE(a, W_)
+            BSI_FOR_NODES(BSI_ZERO_A)
+            if (from_idx) {
+                BSI_PACK(a, cx_)
                 BSI_PREFIX(BSI_LP_ORIGIN)
-            } else {
-                BSI_FOR_NODES(BSI_ZERO_A)
-                if (from_idx) {
-                    BSI_PACK(a, cx_)
-                    BSI_PREFIX(BSI_LP_ORIGIN)
-                    BSI_FOR_NODES(BSI_MASK_A)
-                }
-                if (valid & ~from_idx) {
-                    BSI_PACK(b, cz_)
-                    BSI_FOR_NODES(BSI_OR_AB)
-                }
+                BSI_FOR_NODES(BSI_MASK_A)
+            }
+            if (valid & ~from_idx) {
+                BSI_PACK(b, cz_)
+                BSI_FOR_NODES(BSI_OR_AB)
             }
             BSI_FOR_NODES(BSI_COPY_BC)
 #undef BSI_OR_AB
@@ -1428,9 +1377,6 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                                                 BsiKeep *keep, u32 lanes) {
     {
         u32 todo = 0u;
-        u64 uni_n = 0, uni_s1 = 0, uni_s2 = 0;
-        u32 uni_l0 = 0u;
-        bool have_uni = false;
         if (FROM_KEEP) {
             // same kernel as the mu walk: keys / lambda / c0 were kept, mu - c0 is in aux_s
             todo = lanes;
@@ -1449,51 +1395,9 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
                 }
             }
         }
-        // ---- uniform early word: one key, lambda = 1, c0 = 0 -- no key compares, no group search ---
-        if (FROM_KEEP && todo && keep->uniform) {
-            const u32 l0 = __ffs(todo) - 1;
-            u64 n = 0, s1 = 0, s2 = 0;
-            const bool len_ok = 1ull <= max_attractor_l;          // attract.py:294 with lambda = 1
-#pragma unroll 4
-            for (u32 l = 0; l < 32; ++l) {
-                if (!((todo >> l) & 1u)) continue;
-                const u64 mu = aux_s[l * BSI_BLOCK + threadIdx.x];
-                if (mu + 1ull <= T) {
-                    steps += BSI_LP_ORIGIN + mu + 1ull;
-                    if (len_ok) {
-                        const u64 tl = BSI_LP_ORIGIN + mu;
-                        n += 1; s1 += tl; s2 += tl * tl;
-                    } else {
-                        ++n_rej;
-                    }
-                } else {
-                    steps += stop_t_cap;
-                    ++n_rej;
-                }
-            }
-            n_acc += n;
-            // the word is one group: nothing is left for the group search below.  The warp-level
-            // add is a collective, so it is issued after this block, once, by every thread.
-            if (WARP_AGG) {
-                uni_n = n; uni_s1 = s1; uni_s2 = s2; uni_l0 = l0;
-                have_uni = true;
-            } else if (n) {
-                bsi_table_add(table, log2_slots, keep->key[l0], n, s1, s2, 1u, ctr);
-            }
-            todo = 0u;
-        }
         // ---- acceptance + aggregation (lanes of one thread with equal keys are added once) ------
         // (WARP_AGG: every thread of the warp is here, idle ones with todo == 0, and the loop is
         // warp-uniform so that threads holding the same key can be summed before the atomics)
-        if (WARP_AGG) {
-            // the uniform threads' totals first (collective: every thread of the warp takes part)
-            if (__any_sync(0xFFFFFFFFu, have_uni)) {
-                u64 key0[BSI_KW];
-#pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) key0[i] = have_uni ? keep->key[uni_l0][i] : 0ull;
-                bsi_warp_table_add(table, log2_slots, key0, have_uni ? uni_n : 0ull, uni_s1, uni_s2, 1u, ctr);
-            }
-        }
         // acceptance of every lane first, each lane on its own (independent iterations: their local-
         // and shared-memory loads overlap, where a loop over "the remaining lanes with this key" makes
         // every load wait for the one before): ok = lanes whose attractor counts, tl_ = their
@@ -1568,6 +1472,314 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 //    trajectory kernel -- bsi_resolve runs the mu walks and the key walks side by side (first
 //    and second half of its task range; tasks are handed out 32 at a time, so a warp is never
 //    split between the two), then bsi_resolve_finish aggregates.
+#if BSI_UNIT != 3
+// ---------------------------------------------------------------------------------------------
+// early words: resolution per EVENT and per GROUP, not per lane
+// ---------------------------------------------------------------------------------------------
+// An entry of the early-word queue is a dense word (all lanes start from the problem-index word, c0 =
+// 0), its state y at time j_end -- an on-cycle state of every handed-over lane -- and its match
+// events (lanes, lambda).  What the reference computes per trajectory (attract.py:287-300) comes out
+// of three bit-sliced passes with no per-lane scalar work:
+//   keys    the lexicographic minimum over the cycle, walked from y for max lambda - 1 steps; the same
+//           walk latches P(0) = y advanced by (lambda - j_end mod lambda) mod lambda steps, event by
+//           event (long cycles: both from the cycle dictionary instead);
+//   groups  lanes with equal keys, found by broadcasting one lane's key bits against all lanes
+//           (2 ops per node and group; the ordered regime has a handful of groups per word);
+//   mu      the lock-step of x_j (from the index word) and P(j); the lanes that agree first at
+//           step j add (count, count * j, count * j^2) to their groups -- one popc per group.
+// Only then the table is touched, once per group.
+struct BsiGroups {
+    u32 n_groups;
+    u32 mask[32];               // lanes of the group
+    u32 lam[32];                // their cycle length
+    u64 key[32][BSI_KW];        // their canonical key
+    u64 n[32], s1[32], s2[32];  // accepted lanes, sum and sum of squares of their trajectory lengths
+};
+
+// lanes m reached their cycle at relative time j: acceptance (mu + lambda <= T, lambda <=
+// max_attractor_l; reference attract.py:287-300, model.py:201) and the groups' sums
+__device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u64 j, u64 T, u64 max_attractor_l,
+                                               u64 stop_t_cap, u64 &steps, u64 &n_rej) {
+#pragma unroll 1
+    for (u32 g = 0; g < gr.n_groups; ++g) {
+        const u64 cnt = __popc(m & gr.mask[g]);
+        if (!cnt) continue;
+        const u64 lam = gr.lam[g];
+        if (j + lam <= T) {                              // the loop stops at t = mu + lambda (model.py:201)
+            steps += cnt * (BSI_LP_ORIGIN + j + lam);
+            if (lam <= max_attractor_l) {                // attract.py:294
+                const u64 tl = BSI_LP_ORIGIN + j;        // trajectory_l, attract.py:298
+                gr.n[g] += cnt;
+                gr.s1[g] += cnt * tl;
+                gr.s2[g] += cnt * tl * tl;
+            } else {
+                n_rej += cnt;
+            }
+        } else {                                         // closes only after max_t
+            steps += cnt * stop_t_cap;
+            n_rej += cnt;
+        }
+    }
+}
+
+// The cycle dictionary's part of an early word (OUT OF LINE: words of short cycles never come here):
+// state codes of y by one transpose pass, lookups of the lanes on cycles, then P(0) bit-sliced into
+// pb and the groups -- lanes on cycles by where their orbit is stored (one number per attractor),
+// fixed points by their state code.  false: some cycle is not in the dictionary (nothing is filled).
+__device__ __noinline__ bool bsi_early_dict(const BsiDict &dict, const u32 *y, u32 valid, u32 n_ev, const u32 *evm,
+                                            const u32 *evl, const u32 *eva, u32 *pb, BsiGroups &gr) {
+    u64 cw_[32][BSI_KW];
+    u32 lam_[32], adv_[32], dbase_[32];
+    {
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_LOAD_MEM(b, y, 32)
+        BSI_UNPACK(cw_, b)
+    }
+#pragma unroll 1
+    for (u32 l = 0; l < 32; ++l) { lam_[l] = 0u; adv_[l] = 0u; }
+#pragma unroll 1
+    for (u32 k = 0; k < n_ev; ++k) {
+        u32 m = evm[k];
+        while (m) {
+            const u32 l = __ffs(m) - 1;
+            m &= m - 1;
+            lam_[l] = evl[k];
+            adv_[l] = eva[k];
+        }
+    }
+    u64 keys_[32][BSI_KW];
+    if (bsi_dict_word(dict, cw_, lam_, adv_, 1u, true, keys_, pb, dbase_)) return false;
+    u32 todo = valid, G = 0u;
+    while (todo) {
+        const u32 l0 = __ffs(todo) - 1;
+        const bool cyc = lam_[l0] > 1u;
+        u32 g = 0u;
+#pragma unroll 4
+        for (u32 l = 0; l < 32; ++l) {
+            bool same;
+            if (cyc) {
+                same = lam_[l] > 1u && dbase_[l] == dbase_[l0];
+            } else {
+                same = lam_[l] == 1u;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) same = same && cw_[l][i] == cw_[l0][i];
+            }
+            g |= (same ? 1u : 0u) << l;
+        }
+        g &= todo;
+        todo &= ~g;
+        gr.mask[G] = g;
+        gr.lam[G] = lam_[l0];
+#pragma unroll
+        for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = cyc ? keys_[l0][i] : cw_[l0][i];
+        gr.n[G] = 0ull; gr.s1[G] = 0ull; gr.s2[G] = 0ull;
+        ++G;
+    }
+    gr.n_groups = G;
+    return true;
+}
+
+// One entry of the early-word queue (`have`: this thread has one; with WARP_AGG every thread of the
+// warp must call, idle ones with have = false, because the table adds are warp collectives).
+template <bool WARP_AGG>
+__device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool have, u64 T, u64 max_attractor_l,
+                                               u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr,
+                                               const BsiDict &dict, bool learn, u64 &steps, u64 &n_acc,
+                                               u64 &n_rej) {
+    BsiGroups gr;
+    gr.n_groups = 0u;
+    if (have) {
+        BSI_FOR_NODES(BSI_DECL_A)
+        BSI_FOR_NODES(BSI_DECL_B)
+        BSI_FOR_NODES(BSI_DECL_C)
+        const BsiEarlyEntry ent = bsi_early_entry(eq, e);
+        const u32 valid = ent.mask[0];
+        const u32 info = ent.info[0];
+        const u32 n_ev = info & 0xFFu, j_end = info >> 8;
+        const u64 W_ = ent.word[0];
+        u32 evm[32], evl[32], eva[32];
+        // (all event loads first, independent and in flight together)
+#pragma unroll 8
+        for (u32 k = 0; k < 32; ++k)
+            if (k < n_ev) { evm[k] = ent.evm[k * 32u]; evl[k] = ent.evl[k * 32u]; }
+        u32 lam_max = 0u, next_ = 0xFFFFFFFFu;
+#pragma unroll 1
+        for (u32 k = 0; k < n_ev; ++k) {
+            const u32 lam = evl[k];
+            // (fixed points, the bulk of the ordered regime, need no division)
+            const u32 adv = lam == 1u ? 0u : (lam - j_end % lam) % lam;
+            eva[k] = adv;
+            lam_max = max(lam_max, lam);
+            if (adv) next_ = min(next_, adv);
+        }
+        u32 pb_[BSI_N];                                  // P(0), bit-sliced (cycles only)
+        bool via_dict = false;
+        if (lam_max > BSI_DICT_MIN_LAM && dict.slots) {
+            via_dict = bsi_early_dict(dict, ent.y, valid, n_ev, evm, evl, eva, pb_, gr);
+            if (via_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) }
+        }
+        if (!via_dict) {
+            BSI_LOAD_MEM(b, ent.y, 32)
+            BSI_FOR_NODES(BSI_COPY_CB_)
+            if (lam_max > 1u) {
+                // ---- keys (running minimum in c) and P(0) (latched into pb_) in one walk from y -----
+#define BSI_LEX_NODE(i)                                                           \
+    lt_ |= bsi_lop3<0x08>(X_(i), c##i, eq_);                                      \
+    eq_ = bsi_lop3<0x90>(eq_, X_(i), c##i);
+#define BSI_SEL_NODE(i) c##i = bsi_lop3<0xCA>(lt_, X_(i), c##i);
+#define BSI_LATCH_NODE(i) pb_[i] = bsi_lop3<0xCA>(m_, X_(i), pb_[i]);
+                // state X is y advanced by K steps: minimum, then the events whose P(0) it is
+#define BSI_EW_STEP(K)                                                            \
+    {                                                                             \
+        u32 lt_ = 0u, eq_ = valid;                                                \
+        BSI_LEX_CHUNKS                                                            \
+        if (lt_) { BSI_FOR_NODES(BSI_SEL_NODE) }                                  \
+        if ((K) == next_) {                                                       \
+            u32 m_ = 0u, nx_ = 0xFFFFFFFFu;                                       \
+            _Pragma("unroll 1")                                                   \
+            for (u32 q_ = 0; q_ < n_ev; ++q_) {                                   \
+                const u32 adv_ = eva[q_];                                         \
+                if (adv_ == (K)) m_ |= evm[q_];                                   \
+                else if (adv_ > (K)) nx_ = min(nx_, adv_);                        \
+            }                                                                     \
+            next_ = nx_;                                                          \
+            BSI_FOR_NODES(BSI_LATCH_NODE)                                         \
+        }                                                                         \
+    }
+                BSI_STORE_ALL(b, pb_, 1)                 // (advance 0: P(0) = y)
+                for (u32 k = 1; k < lam_max; k += 2) {
+                    BSI_UPDATE(a, b)
+#define X_(i) a##i
+                    BSI_EW_STEP(k)
+#undef X_
+                    if (k + 1u >= lam_max) break;
+                    BSI_UPDATE(b, a)
+#define X_(i) b##i
+                    BSI_EW_STEP(k + 1u)
+#undef X_
+                }
+#undef BSI_EW_STEP
+#undef BSI_LATCH_NODE
+#undef BSI_SEL_NODE
+#undef BSI_LEX_NODE
+            }
+            // ---- groups: lanes whose key equals that of the first lane left ---------------------------
+            u32 todo = valid, G = 0u;
+            while (todo) {
+                const u32 l0 = __ffs(todo) - 1;
+                const u32 sh_ = 31u - l0;
+                u32 diff_ = 0u;
+                u32 kc_[2 * BSI_KW];
+#pragma unroll
+                for (int i = 0; i < 2 * BSI_KW; ++i) kc_[i] = 0u;
+                // r_ = the key bit of lane l0 on all lanes (shift it to the sign, then arithmetic shift)
+#define BSI_GRP_NODE(i)                                                           \
+    {                                                                             \
+        const u32 r_ = (u32)((int)(c##i << sh_) >> 31);                           \
+        diff_ = bsi_lop3<0xF6>(diff_, c##i, r_);                                  \
+        kc_[(i) >> 5] |= r_ & (1u << ((i) & 31));                                 \
+    }
+                BSI_FOR_NODES(BSI_GRP_NODE)
+#undef BSI_GRP_NODE
+                const u32 g = ~diff_ & todo;
+                todo &= ~g;
+                u32 lam0 = 1u;
+#pragma unroll 1
+                for (u32 k = 0; k < n_ev; ++k)
+                    if ((evm[k] >> l0) & 1u) lam0 = evl[k];
+                gr.mask[G] = g;
+                gr.lam[G] = lam0;
+#pragma unroll
+                for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = (u64)kc_[2 * i] | ((u64)kc_[2 * i + 1] << 32);
+                gr.n[G] = 0ull; gr.s1[G] = 0ull; gr.s2[G] = 0ull;
+                ++G;
+            }
+            gr.n_groups = G;
+            // the walked cycles go into the dictionary (once per attractor: the claim decides)
+            if (learn && dict.slots && lam_max > BSI_DICT_MIN_LAM) {
+#pragma unroll 1
+                for (u32 g = 0; g < G; ++g) {
+                    u32 base, slot;
+                    // (short cycles too: a word that holds a long one asks the dictionary for all of them)
+                    if (gr.lam[g] > 1u && bsi_dict_claim(dict, gr.key[g], gr.lam[g], base, slot))
+                        bsi_dict_learn(dict, gr.key[g], gr.lam[g], base, slot);
+                }
+            }
+        }
+        // ---- a <- x_0 from the problem-index word, b <- P(0) -------------------------------------
+        BSI_INIT_DENSE(a, W_)
+        BSI_PREFIX(BSI_LP_ORIGIN)
+        if (lam_max > 1u) { BSI_LOAD_MEM(b, pb_, 1) } else { BSI_LOAD_MEM(b, ent.y, 32) }
+        // ---- lock-step: mu = first j with x_j == P(j) -------------------------------------------
+        u32 alive = valid;
+#define BSI_LOCK_CMP(A, B, J)                                                     \
+    {                                                                             \
+        u32 p_ = ~alive, q_ = 0u;                                                 \
+        BSI_CMP_FILTER(p_, q_, A, B)                                              \
+        p_ |= q_;                                                                 \
+        if (p_ != 0xFFFFFFFFu) {                                                  \
+            BSI_CMP_REST(p_, A, B)                                                \
+            const u32 m_ = ~p_;                                                   \
+            if (m_) {                                                             \
+                alive &= ~m_;                                                     \
+                bsi_early_account(gr, m_, (J), T, max_attractor_l, stop_t_cap, steps, n_rej); \
+            }                                                                     \
+        }                                                                         \
+    }
+#define BSI_LOCK(A, B, Tn, J)                                                     \
+    {                                                                             \
+        BSI_LOCK_CMP(A, B, J)                                                     \
+        if (alive) { BSI_UPDATE(Tn, A) BSI_UPDATE(A, B) }                         \
+    }
+        if (lam_max <= 1u) {
+            // every lane ends in a fixed point: P is constant (= b), only x moves (a <-> c)
+            u32 j = 0;
+            while (alive && j <= j_end) {
+                BSI_LOCK_CMP(a, b, j)
+                if (!alive || j + 1 > j_end) break;
+                BSI_UPDATE(c, a)
+                BSI_LOCK_CMP(c, b, j + 1)
+                if (!alive || j + 2 > j_end) break;
+                BSI_UPDATE(a, c)
+                j += 2;
+            }
+        } else {
+            u32 j = 0;
+            while (alive && j <= j_end) {
+                BSI_LOCK(a, b, c, j)
+                if (!alive || j + 1 > j_end) break;
+                BSI_LOCK(c, a, b, j + 1)
+                if (!alive || j + 2 > j_end) break;
+                BSI_LOCK(b, c, a, j + 2)
+                j += 3;
+            }
+        }
+#undef BSI_LOCK
+#undef BSI_LOCK_CMP
+        if (alive) atomicExch(&ctr->internal_error, 1ull);
+#pragma unroll 1
+        for (u32 g = 0; g < gr.n_groups; ++g) n_acc += gr.n[g];
+    }
+    // ---- the table, once per group ---------------------------------------------------------------
+    if (WARP_AGG) {
+        const u32 g_max = __reduce_max_sync(0xFFFFFFFFu, gr.n_groups);
+#pragma unroll 1
+        for (u32 g = 0; g < g_max; ++g) {
+            const bool mine = g < gr.n_groups;
+            u64 key0[BSI_KW];
+#pragma unroll
+            for (int i = 0; i < BSI_KW; ++i) key0[i] = mine ? gr.key[g][i] : 0ull;
+            bsi_warp_table_add(table, log2_slots, key0, mine ? gr.n[g] : 0ull, mine ? gr.s1[g] : 0ull,
+                               mine ? gr.s2[g] : 0ull, mine ? gr.lam[g] : 0u, ctr);
+        }
+    } else {
+#pragma unroll 1
+        for (u32 g = 0; g < gr.n_groups; ++g)
+            if (gr.n[g]) bsi_table_add(table, log2_slots, gr.key[g], gr.n[g], gr.s1[g], gr.s2[g], gr.lam[g], ctr);
+    }
+}
+#endif  // BSI_UNIT != 3
+
 #if BSI_UNIT != 5 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u64 max_attractor_l,
@@ -1578,13 +1790,12 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
     const u64 n_words = BSI_QWORDS(n_found);
     u64 steps = 0, n_acc = 0, n_rej = 0;
     BsiKeep keep;
-    const BsiEarlyQ no_early = bsi_early_view(nullptr, 0);
     for (;;) {
         const u64 w = bsi_grab_word(&ctr->next_word3);
         if (__all_sync(0xFFFFFFFFu, w >= n_words)) break;
         u32 lanes = 0u;                  // threads without a word stay for the warp-level aggregation
         if (w < n_words && BSI_Q(w, 0) < n_found)
-            bsi_mu_word<false, true, false>(found_q, n_found, w, aux_s, ctr, &keep, no_early, dict, true, lanes);
+            bsi_mu_word<false, true>(found_q, n_found, w, aux_s, ctr, &keep, dict, true, lanes);
         __syncwarp();
         bsi_finish_word<true, true>(found_q, n_found, w, T, max_attractor_l, stop_t_cap, table, log2_slots,
                                     ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
@@ -1635,27 +1846,22 @@ extern "C" __global__ void bsi_dict_learn_keys(const u64 *keys, const u64 *lams,
 
 #endif  // BSI_UNIT != 5
 #if BSI_UNIT == 0 || BSI_UNIT == 6
-// The early-word queue of a dense round: keys, mu and aggregation of lanes that matched an early
-// checkpoint, straight from their bit-sliced states (no records, one transpose pass per word).
+// The early-word queue of a dense round: keys, mu and aggregation of the lanes that matched an early
+// checkpoint, straight from the word's bit-sliced state (see bsi_early_word).
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u64 *n_found_p,
                   u64 few_words, u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
                   u32 log2_slots, BsiCounters *ctr, const BsiDict dict) {
-    __shared__ u32 aux_s[32 * BSI_BLOCK];
     const u64 n_early = *n_early_p;
     if (n_early == 0) return;
     if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
-    BsiKeep keep;
     for (;;) {
         const u64 e = bsi_grab_word(&ctr->next_word4);
         if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
-        u32 lanes = 0u;
-        if (e < n_early) bsi_mu_word<false, true, true>(nullptr, 0, e, aux_s, ctr, &keep, eq, dict, true, lanes);
-        __syncwarp();
-        bsi_finish_word<true, true>(nullptr, 0, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
-                                    steps, n_acc, n_rej, aux_s, &keep, lanes);
+        bsi_early_word<true>(eq, e, e < n_early, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict,
+                             true, steps, n_acc, n_rej);
     }
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
@@ -1684,18 +1890,14 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
             if (BSI_Q(t, 0) < n_found) {
                 u32 lanes = 0u;
                 BsiKeep keep;
-                bsi_mu_word<true, false, false>(found_q, n_found, t, aux_s, ctr, &keep,
-                                                bsi_early_view(nullptr, 0), dict, false, lanes);
+                bsi_mu_word<true, false>(found_q, n_found, t, aux_s, ctr, &keep, dict, false, lanes);
             }
         } else if (t < 2 * w32) {
             if (BSI_Q(t - w32, 0) < n_found) bsi_key_word(found_q, n_found, t - w32, dict);
         } else if (t - 2 * w32 < n_early) {
-            BsiKeep keep;
-            u32 lanes = 0u;
             // (no learning on the latency-oriented path: see bsi_key_word)
-            bsi_mu_word<false, true, true>(nullptr, 0, t - 2 * w32, aux_s, ctr, &keep, eq, dict, false, lanes);
-            bsi_finish_word<true, false>(nullptr, 0, t - 2 * w32, T, max_attractor_l, stop_t_cap, table,
-                                  log2_slots, ctr, steps, n_acc, n_rej, aux_s, &keep, lanes);
+            bsi_early_word<false>(eq, t - 2 * w32, true, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
+                                  dict, false, steps, n_acc, n_rej);
         }
     }
     if (steps) atomicAdd(&ctr->steps, steps);

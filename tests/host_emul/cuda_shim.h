@@ -86,6 +86,15 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     bsi_rendezvous();
     return r;
 }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    const unsigned lane = threadIdx.x & 31u;
+    bsi_warp_slot[lane] = v;
+    bsi_rendezvous();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) r = r > (unsigned)bsi_warp_slot[l] ? r : (unsigned)bsi_warp_slot[l];
+    bsi_rendezvous();
+    return r;
+}
 
 // one block of n_threads threads (a multiple of 32, at most 32 * BSI_EMUL_MAX_WARPS) runs `kernel`
 #include <functional>

@@ -53,13 +53,13 @@ int main(int argc, char **argv) {
     }
     const u64 T = max_t == INF ? INF : max_t - lp;
     const u64 kMaxH = 1ull << 30;
-    u32 *scratch = device_alloc<u32>((size_t)BSI_BLOCK * (96 + 3 * BSI_N));
+    u32 *scratch = device_alloc<u32>((size_t)BSI_BLOCK * (BSI_SCRATCH_WORDS + 3 * BSI_N));
     const u64 b = idx_begin, e = idx_end;
     const u64 n_lanes = e - b;
     BsiFound *found_q = device_alloc<BsiFound>(n_lanes + 64 + 1024);
     u64 *retry_q[2] = {device_alloc<u64>(n_lanes + 64), device_alloc<u64>(n_lanes + 64)};
     const u64 word0 = b >> 5, n_words_dense = ((e + 31) >> 5) - word0;
-    void *early_q = calloc(((n_words_dense + 31) / 32) * 32 * (8 + 4 + 32 * 8 + 4 * (size_t)BSI_N) + 64, 1);
+    void *early_q = calloc(((n_words_dense + 31) / 32) * BSI_EQ_BLOCK_BYTES + 64, 1);
 
     // cycle dictionary (argv[9]: 1 = off; log2 of the orbit storage in argv[10], default 12)
     const int no_dict = argc > 9 ? atoi(argv[9]) : 0;

@@ -312,3 +312,28 @@ def test_emulated_cycle_dictionary(block_threads, tmp_path):
                  dict(few_words=1, dict_log2=6), dict(few_words=1, first_horizon=8), {}):
         _check(exe, space, 0, pk.n_problems, 1000, inf, **opts)
     _check(exe, space, 100, 3001, 90, 30, few_words=1)
+
+
+def test_emulated_early_words_of_the_cambium_network(tmp_path):
+    """cambium2 (30 nodes, every state an initial state): two thirds of the lanes end in fixed points,
+    the rest on cycles of length 2 to 18 -- words that mix fixed points, walked cycles and, with the
+    18-cycle, the dictionary; the event / group resolution of the early-word queue in the throughput
+    and the latency form, with and without caps, on ragged ranges spread over the 2^30 states."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
+    import codec
+    from boolsi_b200.constants import NodeStateRange
+    pub = codec.load('published.json')
+    _, preds, tts = codec.decode_network(codec.load('networks.json')['networks']['cambium'])
+    origin, variations = codec.decode_problem(pub['cambium2_problem'], NodeStateRange)
+    args = (preds, tts, origin, variations)
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk)
+    for lo, n, max_t, max_a, opts in ((0, 4096, inf, inf, dict(few_words=1)),
+                                      (123456789, 3001, inf, inf, dict(few_words=1)),
+                                      (700000003, 2500, 12, 6, dict(few_words=1)),
+                                      (1000000000, 2048, inf, inf, {}),
+                                      (1073741824 - 1500, 1500, inf, inf, dict(few_words=1, first_horizon=6)),
+                                      (5, 2000, inf, inf, dict(few_words=1, no_dict=1))):
+        _check(exe, space, lo, lo + n, max_t, max_a, table_log2=10, **opts)
