@@ -540,11 +540,18 @@ int compile_plan(bsi_plan *p) {
     // cycle, 32 lookups + gathers + the 32x32 transposes about 2800 instructions.
     const int walk_per_step = 2 * std::max(1, p->m.n) + 4 * p->m.n;      // (U <= N for K <= 3; a bound is enough)
     const int dict_min_lam = std::max(8, 2800 / walk_per_step);
+    // Early words get keys AND P(0) out of ONE walk of max lambda - 1 steps, each an update plus the
+    // bit-sliced minimum (about U + 2 N + 10 instructions), while their way through the dictionary --
+    // transposes to state codes, per-lane lookups and gathers, transposes back -- costs about 8000
+    // (measured on cambium2, where the 18-cycle sat just above the old common threshold: the 6 % of
+    // the words that held one took 12 % of the kernel's instructions).
+    const int early_dict_min_lam = std::max(8, 8000 / (3 * p->m.n + 10));
     p->smem_slots = p->opts.smem_slots ? (int)p->opts.smem_slots : 3;
     if (p->smem_slots < 1 || p->smem_slots > 3) return fail(BSI_E_ARG, "smem_slots must be 1, 2 or 3");
     const std::string header = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info) +
                                "#define BSI_SMEM_SLOTS " + std::to_string(p->smem_slots) + "\n" +
                                "#define BSI_DICT_MIN_LAM " + std::to_string(dict_min_lam) + "u\n" +
+                               "#define BSI_EARLY_DICT_MIN_LAM " + std::to_string(early_dict_min_lam) + "u\n" +
                                "#define BSI_TUNE " + std::to_string(p->opts.tune) + "\n";
     p->source = header + "\n#line 1 \"bsi_template.cuh\"\n" + bsi_template_src;
     tm.lap("generate source");

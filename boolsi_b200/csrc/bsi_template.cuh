@@ -1493,33 +1493,93 @@ struct BsiGroups {
     u32 mask[32];               // lanes of the group
     u32 lam[32];                // their cycle length
     u64 key[32][BSI_KW];        // their canonical key
-    u64 n[32], s1[32], s2[32];  // accepted lanes, sum and sum of squares of their trajectory lengths
+    u64 jlim[32];               // a lane of the group that reaches its cycle at relative time j closes by
+                                // max_t iff j < jlim (mu + lambda <= T, reference model.py:201)
+    u32 n[32], late[32];        // lanes that close in time / only after max_t
+    u32 s1[32];                 // sum of j over the former (j < 2^24, at most 32 lanes)
+    u64 s2[32];                 // sum of j^2
 };
+__device__ __forceinline__ void bsi_group_open(BsiGroups &gr, u32 g, u32 mask, u32 lam, u64 T) {
+    gr.mask[g] = mask;
+    gr.lam[g] = lam;
+    gr.jlim[g] = (u64)lam <= T ? T - lam + 1ull : 0ull;
+    gr.n[g] = 0u; gr.late[g] = 0u; gr.s1[g] = 0u; gr.s2[g] = 0ull;
+}
 
-// lanes m reached their cycle at relative time j: acceptance (mu + lambda <= T, lambda <=
-// max_attractor_l; reference attract.py:287-300, model.py:201) and the groups' sums
-__device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u64 j, u64 T, u64 max_attractor_l,
-                                               u64 stop_t_cap, u64 &steps, u64 &n_rej) {
+// lanes m reached their cycle at relative time j: one popc per group
+__device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
 #pragma unroll 1
     for (u32 g = 0; g < gr.n_groups; ++g) {
-        const u64 cnt = __popc(m & gr.mask[g]);
+        const u32 cnt = __popc(m & gr.mask[g]);
         if (!cnt) continue;
-        const u64 lam = gr.lam[g];
-        if (j + lam <= T) {                              // the loop stops at t = mu + lambda (model.py:201)
-            steps += cnt * (BSI_LP_ORIGIN + j + lam);
-            if (lam <= max_attractor_l) {                // attract.py:294
-                const u64 tl = BSI_LP_ORIGIN + j;        // trajectory_l, attract.py:298
-                gr.n[g] += cnt;
-                gr.s1[g] += cnt * tl;
-                gr.s2[g] += cnt * tl * tl;
-            } else {
-                n_rej += cnt;
-            }
-        } else {                                         // closes only after max_t
-            steps += cnt * stop_t_cap;
-            n_rej += cnt;
+        if ((u64)j < gr.jlim[g]) {
+            const u32 cj = cnt * j;
+            gr.n[g] += cnt;
+            gr.s1[g] += cj;
+            gr.s2[g] += (u64)cj * j;
+        } else {
+            gr.late[g] += cnt;
         }
     }
+}
+
+// Per-thread cache of the attractors its last words fell into: (key, lambda) -> (n, sum, sum of squares)
+// of trajectory lengths, added up locally and only written to the table when an entry is evicted
+// and when the kernel ends.  In the ordered regime millions of lanes fall into a handful of
+// attractors: consecutive words of a thread hit the same few keys, so a group costs a key compare
+// and three additions instead of a table probe and three atomics on one of a few hot L2 addresses
+// (or the warp-wide aggregation that kept those atomics apart before).
+#define BSI_TC_WAYS 4
+struct BsiTCache {
+    u64 key[BSI_TC_WAYS][BSI_KW];
+    u64 n[BSI_TC_WAYS], s1[BSI_TC_WAYS], s2[BSI_TC_WAYS];
+    u32 lam[BSI_TC_WAYS];
+    u32 used, victim;
+};
+__device__ __forceinline__ void bsi_tcache_init(BsiTCache &tc) { tc.used = 0u; tc.victim = 0u; }
+__device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n, u64 s1, u64 s2, u32 lam,
+                                            BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+#pragma unroll 1
+    for (u32 i = 0; i < tc.used; ++i) {
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < BSI_KW; ++k) same = same && tc.key[i][k] == key[k];
+        if (same) {
+            tc.n[i] += n; tc.s1[i] += s1; tc.s2[i] += s2;
+            return;
+        }
+    }
+    u32 i = tc.used;
+    if (i < BSI_TC_WAYS) {
+        tc.used = i + 1u;
+    } else {
+        i = tc.victim;
+        tc.victim = (i + 1u) % BSI_TC_WAYS;
+        bsi_table_add(table, log2_slots, tc.key[i], tc.n[i], tc.s1[i], tc.s2[i], tc.lam[i], ctr);
+    }
+#pragma unroll
+    for (int k = 0; k < BSI_KW; ++k) tc.key[i][k] = key[k];
+    tc.n[i] = n; tc.s1[i] = s1; tc.s2[i] = s2; tc.lam[i] = lam;
+}
+// the end of the kernel: with WARP_AGG a warp collective (every thread of the warp calls), entry by
+// entry, so that the threads of a warp that hold the same key write it once
+template <bool WARP_AGG>
+__device__ __forceinline__ void bsi_tcache_flush(BsiTCache &tc, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
+#pragma unroll 1
+    for (u32 i = 0; i < BSI_TC_WAYS; ++i) {
+        const bool mine = i < tc.used;
+        if (WARP_AGG) {
+            if (!__any_sync(0xFFFFFFFFu, mine)) break;
+            u64 key0[BSI_KW];
+#pragma unroll
+            for (int k = 0; k < BSI_KW; ++k) key0[k] = mine ? tc.key[i][k] : 0ull;
+            bsi_warp_table_add(table, log2_slots, key0, mine ? tc.n[i] : 0ull, mine ? tc.s1[i] : 0ull,
+                               mine ? tc.s2[i] : 0ull, mine ? tc.lam[i] : 0u, ctr);
+        } else if (mine) {
+            bsi_table_add(table, log2_slots, tc.key[i], tc.n[i], tc.s1[i], tc.s2[i], tc.lam[i], ctr);
+        }
+    }
+    tc.used = 0u;
 }
 
 // The cycle dictionary's part of an early word (OUT OF LINE: words of short cycles never come here):
@@ -1527,7 +1587,7 @@ __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u64 j, u64 
 // pb and the groups -- lanes on cycles by where their orbit is stored (one number per attractor),
 // fixed points by their state code.  false: some cycle is not in the dictionary (nothing is filled).
 __device__ __noinline__ bool bsi_early_dict(const BsiDict &dict, const u32 *y, u32 valid, u32 n_ev, const u32 *evm,
-                                            const u32 *evl, const u32 *eva, u32 *pb, BsiGroups &gr) {
+                                            const u32 *evl, const u32 *eva, u32 *pb, BsiGroups &gr, u64 T) {
     u64 cw_[32][BSI_KW];
     u32 lam_[32], adv_[32], dbase_[32];
     {
@@ -1554,41 +1614,40 @@ __device__ __noinline__ bool bsi_early_dict(const BsiDict &dict, const u32 *y, u
         const u32 l0 = __ffs(todo) - 1;
         const bool cyc = lam_[l0] > 1u;
         u32 g = 0u;
+        if (cyc) {
+            // (independent loads, all in flight together)
+            const u32 b0 = dbase_[l0];
+#pragma unroll
+            for (u32 l = 0; l < 32; ++l) g |= ((lam_[l] > 1u && dbase_[l] == b0) ? 1u : 0u) << l;
+        } else {
 #pragma unroll 4
-        for (u32 l = 0; l < 32; ++l) {
-            bool same;
-            if (cyc) {
-                same = lam_[l] > 1u && dbase_[l] == dbase_[l0];
-            } else {
-                same = lam_[l] == 1u;
+            for (u32 l = 0; l < 32; ++l) {
+                bool same = lam_[l] == 1u;
 #pragma unroll
                 for (int i = 0; i < BSI_KW; ++i) same = same && cw_[l][i] == cw_[l0][i];
+                g |= (same ? 1u : 0u) << l;
             }
-            g |= (same ? 1u : 0u) << l;
         }
         g &= todo;
         todo &= ~g;
-        gr.mask[G] = g;
-        gr.lam[G] = lam_[l0];
+        bsi_group_open(gr, G, g, lam_[l0], T);
 #pragma unroll
         for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = cyc ? keys_[l0][i] : cw_[l0][i];
-        gr.n[G] = 0ull; gr.s1[G] = 0ull; gr.s2[G] = 0ull;
         ++G;
     }
     gr.n_groups = G;
     return true;
 }
 
-// One entry of the early-word queue (`have`: this thread has one; with WARP_AGG every thread of the
-// warp must call, idle ones with have = false, because the table adds are warp collectives).
-template <bool WARP_AGG>
-__device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool have, u64 T, u64 max_attractor_l,
+// One entry of the early-word queue.  The groups' totals go into the thread's attractor cache `tc`
+// (the kernel flushes it into the table when it ends).
+__device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T, u64 max_attractor_l,
                                                u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr,
-                                               const BsiDict &dict, bool learn, u64 &steps, u64 &n_acc,
-                                               u64 &n_rej) {
+                                               const BsiDict &dict, bool learn, BsiTCache &tc, u64 &steps,
+                                               u64 &n_acc, u64 &n_rej) {
     BsiGroups gr;
     gr.n_groups = 0u;
-    if (have) {
+    {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
@@ -1614,8 +1673,8 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool 
         }
         u32 pb_[BSI_N];                                  // P(0), bit-sliced (cycles only)
         bool via_dict = false;
-        if (lam_max > BSI_DICT_MIN_LAM && dict.slots) {
-            via_dict = bsi_early_dict(dict, ent.y, valid, n_ev, evm, evl, eva, pb_, gr);
+        if (lam_max > BSI_EARLY_DICT_MIN_LAM && dict.slots) {
+            via_dict = bsi_early_dict(dict, ent.y, valid, n_ev, evm, evl, eva, pb_, gr, T);
             if (via_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) }
         }
         if (!via_dict) {
@@ -1687,16 +1746,14 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool 
 #pragma unroll 1
                 for (u32 k = 0; k < n_ev; ++k)
                     if ((evm[k] >> l0) & 1u) lam0 = evl[k];
-                gr.mask[G] = g;
-                gr.lam[G] = lam0;
+                bsi_group_open(gr, G, g, lam0, T);
 #pragma unroll
                 for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = (u64)kc_[2 * i] | ((u64)kc_[2 * i + 1] << 32);
-                gr.n[G] = 0ull; gr.s1[G] = 0ull; gr.s2[G] = 0ull;
                 ++G;
             }
             gr.n_groups = G;
             // the walked cycles go into the dictionary (once per attractor: the claim decides)
-            if (learn && dict.slots && lam_max > BSI_DICT_MIN_LAM) {
+            if (learn && dict.slots && lam_max > BSI_EARLY_DICT_MIN_LAM) {
 #pragma unroll 1
                 for (u32 g = 0; g < G; ++g) {
                     u32 base, slot;
@@ -1722,7 +1779,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool 
             const u32 m_ = ~p_;                                                   \
             if (m_) {                                                             \
                 alive &= ~m_;                                                     \
-                bsi_early_account(gr, m_, (J), T, max_attractor_l, stop_t_cap, steps, n_rej); \
+                bsi_early_account(gr, m_, (J));                                   \
             }                                                                     \
         }                                                                         \
     }
@@ -1757,26 +1814,31 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, bool 
 #undef BSI_LOCK
 #undef BSI_LOCK_CMP
         if (alive) atomicExch(&ctr->internal_error, 1ull);
-#pragma unroll 1
-        for (u32 g = 0; g < gr.n_groups; ++g) n_acc += gr.n[g];
     }
-    // ---- the table, once per group ---------------------------------------------------------------
-    if (WARP_AGG) {
-        const u32 g_max = __reduce_max_sync(0xFFFFFFFFu, gr.n_groups);
+    // ---- the groups' totals: acceptance (reference attract.py:287-300) and aggregation ----------
 #pragma unroll 1
-        for (u32 g = 0; g < g_max; ++g) {
-            const bool mine = g < gr.n_groups;
-            u64 key0[BSI_KW];
-#pragma unroll
-            for (int i = 0; i < BSI_KW; ++i) key0[i] = mine ? gr.key[g][i] : 0ull;
-            bsi_warp_table_add(table, log2_slots, key0, mine ? gr.n[g] : 0ull, mine ? gr.s1[g] : 0ull,
-                               mine ? gr.s2[g] : 0ull, mine ? gr.lam[g] : 0u, ctr);
+    for (u32 g = 0; g < gr.n_groups; ++g) {
+        const u64 n = gr.n[g], late = gr.late[g], lam = gr.lam[g], s1 = gr.s1[g];
+        steps += n * (BSI_LP_ORIGIN + lam) + s1          // the loop stops at t = mu + lambda (model.py:201)
+                 + late * stop_t_cap;                    // or runs out at max_t
+        n_rej += late;
+        if (lam > max_attractor_l) {                     // attract.py:294
+            n_rej += n;
+        } else if (n) {
+            n_acc += n;
+            // trajectory_l = lp + j (attract.py:298): sums of (lp + j) and (lp + j)^2 from those of j
+            const u64 lp = BSI_LP_ORIGIN;
+            bsi_tcache_add(tc, gr.key[g], n, s1 + n * lp, gr.s2[g] + 2ull * lp * s1 + n * lp * lp, (u32)lam,
+                           table, log2_slots, ctr);
         }
-    } else {
-#pragma unroll 1
-        for (u32 g = 0; g < gr.n_groups; ++g)
-            if (gr.n[g]) bsi_table_add(table, log2_slots, gr.key[g], gr.n[g], gr.s1[g], gr.s2[g], gr.lam[g], ctr);
     }
+}
+// (the latency-oriented kernel holds three kinds of task: this one stays out of its register budget)
+__device__ __noinline__ void bsi_early_word_call(const BsiEarlyQ &eq, u64 e, u64 T, u64 max_attractor_l,
+                                                 u64 stop_t_cap, BsiSlot *table, u32 log2_slots, BsiCounters *ctr,
+                                                 const BsiDict &dict, BsiTCache &tc, u64 &steps, u64 &n_acc,
+                                                 u64 &n_rej) {
+    bsi_early_word(eq, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict, false, tc, steps, n_acc, n_rej);
 }
 #endif  // BSI_UNIT != 3
 
@@ -1857,12 +1919,17 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u
     if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiTCache tc;
+    bsi_tcache_init(tc);
     for (;;) {
         const u64 e = bsi_grab_word(&ctr->next_word4);
         if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
-        bsi_early_word<true>(eq, e, e < n_early, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict,
-                             true, steps, n_acc, n_rej);
+        if (e < n_early)
+            bsi_early_word(eq, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict, true, tc, steps,
+                           n_acc, n_rej);
     }
+    __syncwarp();
+    bsi_tcache_flush<true>(tc, table, log2_slots, ctr);
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
@@ -1883,6 +1950,8 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
     const u64 e32 = (n_early + 31) & ~31ull;
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiTCache tc;
+    bsi_tcache_init(tc);
     for (;;) {
         const u64 t = bsi_grab_word(&ctr->next_word2);
         if (__all_sync(0xFFFFFFFFu, t >= 2 * w32 + e32)) break;
@@ -1896,10 +1965,11 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
             if (BSI_Q(t - w32, 0) < n_found) bsi_key_word(found_q, n_found, t - w32, dict);
         } else if (t - 2 * w32 < n_early) {
             // (no learning on the latency-oriented path: see bsi_key_word)
-            bsi_early_word<false>(eq, t - 2 * w32, true, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr,
-                                  dict, false, steps, n_acc, n_rej);
+            bsi_early_word_call(eq, t - 2 * w32, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict, tc,
+                                steps, n_acc, n_rej);
         }
     }
+    bsi_tcache_flush<false>(tc, table, log2_slots, ctr);
     if (steps) atomicAdd(&ctr->steps, steps);
     if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);

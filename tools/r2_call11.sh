@@ -1,0 +1,16 @@
+#!/bin/bash
+# lighter accounting, thread attractor cache, early dictionary threshold: regimes, quick parity, profiles
+mkdir -p gpurun_out
+python tools/gpu_case.py s0,s1,s2,k2s0,k2s1 26 > gpurun_out/r2_c11_regimes.log 2>&1
+python tools/gpu_case.py c3 26 >> gpurun_out/r2_c11_regimes.log 2>&1
+python tools/gpu_case.py c3 30 >> gpurun_out/r2_c11_regimes.log 2>&1
+cut -c1-60,170-330 gpurun_out/r2_c11_regimes.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "fuzz or published or masters or regime or ordered or large or group" > gpurun_out/r2_c11_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2_c11_tests.log
+tail -n 4 gpurun_out/r2_c11_tests.log
+for c in c3:bsi_resolve_early:early s1:bsi_resolve_early:early s2:bsi_resolve_mu:mu; do
+  case=${c%%:*}; r=${c#*:}; k=${r%%:*}; tag=${r##*:}
+  python tools/gpu_case.py $case 26 '{}' 2 > gpurun_out/r2_c11_plain_$case.log 2>&1 && \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$k" -c 1 -o gpurun_out/r2_c11_prof_${case}_${tag} \
+      python tools/gpu_case.py $case 26 '{}' 2 > gpurun_out/r2_c11_ncu_${case}_${tag}.log 2>&1
+done
+ls -la gpurun_out | grep r2_c11
