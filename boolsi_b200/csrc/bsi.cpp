@@ -197,7 +197,7 @@ struct bsi_plan {
     bsi::Model m;
     bsi::GenInfo info;
     bsi_plan_opts opts{};
-    std::string source, log;
+    std::string source, log, header;       // header: the generated macro header (identifies the plan's units)
     std::shared_ptr<const std::vector<char>> cubins[7];     // per BSI_UNIT (1 dense, 2 queue, 3 + 5 + 6 resolve, 4 the rest)
     int block = 64;
     int device = -1;           // -1: compile-only plan
@@ -212,7 +212,7 @@ struct bsi_plan {
                f_export = nullptr, f_merge = nullptr, f_merge_payloads = nullptr, f_traj = nullptr, f_counts = nullptr, f_learn_keys = nullptr,
                f_target = nullptr;
     int n_sms = 0;
-    int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0, early_blocks_per_sm = 0;
+    int main_blocks_per_sm = 0, key_blocks_per_sm = 0, mu_blocks_per_sm = 0, early_blocks_per_sm = 0, resolve_blocks_per_sm = 0;
     size_t main_smem = 0;
     int smem_slots = 3;
     uint32_t table_log2 = 20;
@@ -503,6 +503,69 @@ void disk_cache_store(const std::string &path, const std::string &header, const 
     if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
 }
 
+// every queue of every run on this plan is short: see bsi_latency_mode in bsi_template.cuh
+bool small_space(const bsi_plan *p) {
+    const uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
+    return p->m.n_problems / 32 + 2 <= few;
+}
+
+// Units already compiled in this process come from the cache without starting a thread.
+int compile_units(bsi_plan *p, const std::vector<int> &units) {
+    const std::string &header = p->header;
+    // the source of a unit = its number + header + template (p->source may already carry the
+    // "#define BSI_UNIT 0" line of bsi_plan_source: the units are built from the parts)
+    const std::string body = header + "\n#line 1 \"bsi_template.cuh\"\n" + bsi_template_src;
+    std::vector<std::pair<int, std::future<UnitResult>>> jobs;
+    {
+        std::lock_guard<std::mutex> lk(g_unit_mu);
+        for (int u : units) {
+            if (p->cubins[u] && !p->cubins[u]->empty()) continue;
+            auto it = g_units.find({header, u});
+            if (it != g_units.end()) {
+                p->cubins[u] = it->second.cubin;
+                p->unit_key[u] = it->second.key;
+                if (!it->second.log.empty()) p->log += it->second.log + "\n";
+                continue;
+            }
+            const std::string unit_key = std::to_string(header.size()) + ":" +
+                                         std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(u);
+            const std::string path = disk_cache_path(header, u);
+            CachedUnit from_disk;
+            if (!path.empty() && disk_cache_load(path, header, &from_disk)) {
+                from_disk.key = unit_key;
+                p->cubins[u] = from_disk.cubin;
+                p->unit_key[u] = unit_key;
+                if (!from_disk.log.empty()) p->log += from_disk.log + "\n";
+                g_units[{header, u}] = std::move(from_disk);
+                continue;
+            }
+            std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + body;
+            jobs.emplace_back(u, std::async(std::launch::async, compile_unit, std::move(src)));
+        }
+    }
+    int rc = BSI_OK;
+    for (auto &job : jobs) {
+        UnitResult r = job.second.get();
+        if (r.status != BSI_OK) {
+            if (rc == BSI_OK) { rc = r.status; g_err = r.error; }
+            continue;
+        }
+        CachedUnit c;
+        c.cubin = std::make_shared<const std::vector<char>>(std::move(r.cubin));
+        c.log = r.log;
+        c.key = std::to_string(header.size()) + ":" + std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(job.first);
+        if (!c.log.empty()) p->log += c.log + "\n";
+        p->cubins[job.first] = c.cubin;
+        p->unit_key[job.first] = c.key;
+        const std::string path = disk_cache_path(header, job.first);
+        if (!path.empty()) disk_cache_store(path, header, c);
+        std::lock_guard<std::mutex> lk(g_unit_mu);
+        if (g_units.size() >= 1024) g_units.clear();
+        g_units[{header, job.first}] = std::move(c);
+    }
+    return rc;
+}
+
 int compile_plan(bsi_plan *p) {
     StageTimer tm;
     const int f_nodes = p->opts.filter_nodes ? (int)p->opts.filter_nodes : 12;
@@ -560,61 +623,72 @@ int compile_plan(bsi_plan *p) {
         return BSI_OK;
     }
 
+    p->header = header;
     // The translation unit is compiled once per BSI_UNIT, in parallel host threads (NVRTC is
-    // thread-safe across programs): the two trajectory kernels dominate the compile time.  Units
-    // already compiled in this process come from the cache without starting a thread.
+    // thread-safe across programs): the two trajectory kernels dominate the compile time.  A SMALL
+    // problem space (every queue of every run is short, so the device always picks the latency-
+    // oriented resolution kernels) only needs the dense trajectory kernel, those kernels and the
+    // rest; the queue kernel and the two throughput-mode resolution kernels are compiled when a run
+    // first needs them (a retry round; ensure_unit).  For a three-node example that halves the cold
+    // start, which is all a job of eight trajectories consists of.
     std::vector<int> units;
-    if (p->m.mode == BSI_MODE_ATTRACT) units = {1, 2, 3, 5, 6, 4}; else units = {4};
-    std::vector<std::pair<int, std::future<UnitResult>>> jobs;
+    if (p->m.mode != BSI_MODE_ATTRACT) units = {4};
+    else if (small_space(p)) units = {1, 5, 4};
+    else units = {1, 2, 3, 5, 6, 4};
     p->log.clear();
-    {
-        std::lock_guard<std::mutex> lk(g_unit_mu);
-        for (int u : units) {
-            auto it = g_units.find({header, u});
-            if (it != g_units.end()) {
-                p->cubins[u] = it->second.cubin;
-                p->unit_key[u] = it->second.key;
-                if (!it->second.log.empty()) p->log += it->second.log + "\n";
-                continue;
-            }
-            const std::string unit_key = std::to_string(header.size()) + ":" +
-                                         std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(u);
-            const std::string path = disk_cache_path(header, u);
-            CachedUnit from_disk;
-            if (!path.empty() && disk_cache_load(path, header, &from_disk)) {
-                from_disk.key = unit_key;
-                p->cubins[u] = from_disk.cubin;
-                p->unit_key[u] = unit_key;
-                if (!from_disk.log.empty()) p->log += from_disk.log + "\n";
-                g_units[{header, u}] = std::move(from_disk);
-                continue;
-            }
-            std::string src = "#define BSI_UNIT " + std::to_string(u) + "\n" + p->source;
-            jobs.emplace_back(u, std::async(std::launch::async, compile_unit, std::move(src)));
-        }
-    }
-    int rc = BSI_OK;
-    for (auto &job : jobs) {
-        UnitResult r = job.second.get();
-        if (r.status != BSI_OK) {
-            if (rc == BSI_OK) { rc = r.status; g_err = r.error; }
-            continue;
-        }
-        CachedUnit c;
-        c.cubin = std::make_shared<const std::vector<char>>(std::move(r.cubin));
-        c.log = r.log;
-        c.key = std::to_string(header.size()) + ":" + std::to_string(std::hash<std::string>()(header)) + ":" + std::to_string(job.first);
-        if (!c.log.empty()) p->log += c.log + "\n";
-        p->cubins[job.first] = c.cubin;
-        p->unit_key[job.first] = c.key;
-        const std::string path = disk_cache_path(header, job.first);
-        if (!path.empty()) disk_cache_store(path, header, c);
-        std::lock_guard<std::mutex> lk(g_unit_mu);
-        if (g_units.size() >= 1024) g_units.clear();
-        g_units[{header, job.first}] = std::move(c);
-    }
+    int rc = compile_units(p, units);
     tm.lap("nvrtc (parallel units)");
     p->source = "#define BSI_UNIT 0\n" + p->source;       // what bsi_plan_source shows: the whole TU
+    return rc;
+}
+
+// loaded modules are kept per (device, unit source) for the life of the process: a later plan
+// for the same network skips cuModuleLoadData / cuModuleUnload (several ms)
+int load_modules(bsi_plan *p) {
+    static std::map<std::string, CUmodule> loaded;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    for (int u = 1; u <= 6; ++u) {
+        if (p->mods[u] || !p->cubins[u] || p->cubins[u]->empty()) continue;
+        const std::string key = std::to_string(p->device) + "/" + p->unit_key[u];
+        auto it = loaded.find(key);
+        if (it != loaded.end()) {
+            p->mods[u] = it->second;
+            p->mod_cached[u] = true;
+            continue;
+        }
+        CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u]->data()));
+        if (loaded.size() < 128) {
+            loaded[key] = p->mods[u];
+            p->mod_cached[u] = true;
+        }
+    }
+    return BSI_OK;
+}
+
+// the kernels of the units that are compiled on demand (see compile_plan)
+int bind_lazy_unit(bsi_plan *p, int u) {
+    int a = 0;
+    if (u == 2 && !p->f_queue) {
+        CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
+        if (p->main_smem > 48 * 1024)
+            CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
+    } else if (u == 3 && !p->f_mu) {
+        CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_mu, p->block, 0));
+        p->mu_blocks_per_sm = std::max(1, a);
+    } else if (u == 6 && !p->f_early) {
+        CU_CHECK(cuModuleGetFunction(&p->f_early, p->mods[6], "bsi_resolve_early"));
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_early, p->block, 0));
+        p->early_blocks_per_sm = std::max(1, a);
+    }
+    return BSI_OK;
+}
+// compile (if this plan skipped it), load and bind unit u: called with the plan's context current
+int ensure_unit(bsi_plan *p, int u) {
+    if (p->mods[u]) return BSI_OK;
+    int rc = compile_units(p, {u});
+    if (rc == BSI_OK) rc = load_modules(p);
+    if (rc == BSI_OK) rc = bind_lazy_unit(p, u);
     return rc;
 }
 
@@ -633,27 +707,7 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->dev));
     if (major != 10) return fail(BSI_E_CUDA, "device %d is sm_%d%d; libbsi kernels are built for sm_100a (B200) only", device, major, minor);
     CU_CHECK(cuDeviceGetAttribute(&p->n_sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->dev));
-    // loaded modules are kept per (device, unit source) for the life of the process: a later plan
-    // for the same network skips cuModuleLoadData / cuModuleUnload (several ms)
-    {
-        static std::map<std::string, CUmodule> loaded;
-        std::lock_guard<std::mutex> lk(g_dev_mu);
-        for (int u = 1; u <= 6; ++u) {
-            if (!p->cubins[u] || p->cubins[u]->empty()) continue;
-            const std::string key = std::to_string(device) + "/" + p->unit_key[u];
-            auto it = loaded.find(key);
-            if (it != loaded.end()) {
-                p->mods[u] = it->second;
-                p->mod_cached[u] = true;
-                continue;
-            }
-            CU_CHECK(cuModuleLoadData(&p->mods[u], p->cubins[u]->data()));
-            if (loaded.size() < 128) {
-                loaded[key] = p->mods[u];
-                p->mod_cached[u] = true;
-            }
-        }
-    }
+    if (int rc1 = load_modules(p)) return rc1;
     tm.lap("cuModuleLoadData");
     CU_CHECK(cuStreamCreate(&p->own_stream, CU_STREAM_NON_BLOCKING));
     p->stream = p->own_stream;
@@ -661,30 +715,28 @@ int load_plan(bsi_plan *p, int device) {
     CU_CHECK(cuModuleGetFunction(&p->f_counts, p->mods[4], "bsi_orbit_counts"));
     if (p->m.mode == BSI_MODE_ATTRACT) {
         CU_CHECK(cuModuleGetFunction(&p->f_dense, p->mods[1], "bsi_attract_dense"));
-        CU_CHECK(cuModuleGetFunction(&p->f_queue, p->mods[2], "bsi_attract_queue"));
         CU_CHECK(cuModuleGetFunction(&p->f_resolve, p->mods[5], "bsi_resolve"));
-        CU_CHECK(cuModuleGetFunction(&p->f_mu, p->mods[3], "bsi_resolve_mu"));
-        CU_CHECK(cuModuleGetFunction(&p->f_learn_keys, p->mods[3], "bsi_dict_learn_keys"));
-        CU_CHECK(cuModuleGetFunction(&p->f_early, p->mods[6], "bsi_resolve_early"));
+        CU_CHECK(cuModuleGetFunction(&p->f_learn_keys, p->mods[5], "bsi_dict_learn_keys"));
         CU_CHECK(cuModuleGetFunction(&p->f_finish, p->mods[5], "bsi_resolve_finish"));
         CU_CHECK(cuModuleGetFunction(&p->f_export, p->mods[4], "bsi_table_export"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge, p->mods[4], "bsi_table_merge"));
         CU_CHECK(cuModuleGetFunction(&p->f_merge_payloads, p->mods[4], "bsi_table_merge_payloads"));
         p->main_smem = (size_t)p->smem_slots * p->m.n * p->block * 4;      // the checkpoint slots held on chip
-        if (p->main_smem > 48 * 1024) {
+        if (p->main_smem > 48 * 1024)
             CU_CHECK(cuFuncSetAttribute(p->f_dense, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
-            CU_CHECK(cuFuncSetAttribute(p->f_queue, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->main_smem));
-        }
-        int a = 0, b = 0;
+        for (int u : {2, 3, 6})
+            if (p->mods[u])
+                if (int rcu = bind_lazy_unit(p, u)) return rcu;
+        // (the persistent grid of both trajectory kernels and the scratch behind it follow the dense
+        //  kernel; the queue kernel takes its work from a counter, so a grid it cannot hold at once
+        //  still finishes)
+        int a = 0;
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_dense, p->block, p->main_smem));
-        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&b, p->f_queue, p->block, p->main_smem));
-        p->main_blocks_per_sm = std::max(1, std::min(a, b));
+        p->main_blocks_per_sm = std::max(1, a);
         CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_finish, p->block, 0));
         p->key_blocks_per_sm = std::max(1, std::min(a, 8));
-        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_mu, p->block, 0));
-        p->mu_blocks_per_sm = std::max(1, a);
-        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_early, p->block, 0));
-        p->early_blocks_per_sm = std::max(1, a);
+        CU_CHECK(cuOccupancyMaxActiveBlocksPerMultiprocessor(&a, p->f_resolve, p->block, 0));
+        p->resolve_blocks_per_sm = std::max(1, a);
         p->table_log2 = p->opts.table_log2_slots ? p->opts.table_log2_slots : 20;
         if (p->table_log2 < 4 || p->table_log2 > 28) return fail(BSI_E_ARG, "table_log2_slots out of range");
         const size_t slot_bytes = (size_t)8 * p->m.kw + 32;
@@ -1022,6 +1074,7 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                 void *args[] = {&in_q, &n_in, &sched, (void *)&final_round, &stop_t, &p->found_q.p,
                                 &retry_out, &p->scratch.p, &p->ctr.p};
                 unsigned grid = (unsigned)std::min<uint64_t>(main_grid, (n_words + p->block - 1) / p->block);
+                if ((rc = ensure_unit(p, 2))) return rc;
                 if ((rc = launch(p, p->f_queue, grid, p->block, p->main_smem, args))) return rc;
             }
             CU_CHECK(cuEventRecord(m1, p->stream));
@@ -1031,13 +1084,18 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
             {
                 CUdeviceptr n_found_p = p->ctr.p + offsetof(Counters, n_found);
                 // all three resolution kernels are launched; the device picks the ones that fit
-                // the queue length (see bsi_template.cuh), the others return at once
+                // the queue length (see bsi_template.cuh), the others return at once -- unless the
+                // round is so small that both queues MUST be short: then the throughput-mode
+                // kernels are not even launched (nor compiled, if the plan has not needed them yet)
                 uint64_t few = p->opts.resolve_few_words ? p->opts.resolve_few_words : 32768;
+                const bool surely_short = n_in / 32 + 2 <= few;
+                if (!surely_short && ((rc = ensure_unit(p, 3)) || (rc = ensure_unit(p, 6)))) return rc;
                 uint64_t t_rel = T, cap_l = max_attractor_l, stop_cap = max_t;
                 void *args_m[] = {&p->found_q.p, &n_found_p, &few, &t_rel, &cap_l, &stop_cap, &p->table.p,
                                   &p->table_log2, &p->ctr.p, &p->dict};
                 unsigned grid_k = (unsigned)(p->n_sms * p->key_blocks_per_sm);
                 unsigned grid_m = (unsigned)(p->n_sms * p->mu_blocks_per_sm);
+                unsigned grid_r = (unsigned)(p->n_sms * p->resolve_blocks_per_sm);
                 uint64_t early_cap = 0;
                 CUdeviceptr early_p = 0;
                 if (dense && !p->opts.no_early_words) {
@@ -1046,12 +1104,14 @@ static int attract_enqueue(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, ui
                     CUdeviceptr n_early_p = p->ctr.p + offsetof(Counters, n_early);
                     void *args_e[] = {&early_p, &early_cap, &n_early_p, &n_found_p, &few, &t_rel, &cap_l,
                                       &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};
-                    if ((rc = launch(p, p->f_early, (unsigned)(p->n_sms * p->early_blocks_per_sm), p->block, 0, args_e))) return rc;
+                    if (!surely_short &&
+                        (rc = launch(p, p->f_early, (unsigned)(p->n_sms * p->early_blocks_per_sm), p->block, 0, args_e)))
+                        return rc;
                 }
                 void *args_r[] = {&p->found_q.p, &n_found_p, &few, &early_p, &early_cap, &t_rel, &cap_l,
                                   &stop_cap, &p->table.p, &p->table_log2, &p->ctr.p, &p->dict};
-                if ((rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
-                if ((rc = launch(p, p->f_resolve, grid_m, p->block, 0, args_r))) return rc;
+                if (!surely_short && (rc = launch(p, p->f_mu, grid_m, p->block, 0, args_m))) return rc;
+                if ((rc = launch(p, p->f_resolve, grid_r, p->block, 0, args_r))) return rc;
                 if ((rc = launch(p, p->f_finish, grid_k, p->block, 0, args_m))) return rc;
             }
             CU_CHECK(cuEventRecord(r1, p->stream));

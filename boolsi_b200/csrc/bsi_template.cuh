@@ -212,6 +212,19 @@ __device__ __forceinline__ u64 bsi_hash_key(const u64 *k) {
     return h;
 }
 
+// flag of a table slot, with acquire semantics: what its writer stored before the release (key,
+// lambda) is visible after it -- no fence on the reader's side (a membar.gl per table update was a
+// quarter of the early-word kernel's stall samples)
+__device__ __forceinline__ u32 bsi_ld_acquire_u32(const u32 *p) {
+#ifdef BSI_HOST_EMUL
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
 // Adds (n, s1, s2) for `key` to the open-addressing table (the replacement for the ZODB store and
 // the Welford/Chan merges of reference attract.py:35-45, 405-455: integer sums are exact and
 // order-independent).
@@ -222,7 +235,7 @@ __device__ __noinline__ void bsi_table_add(BsiSlot *table, u32 log2_slots, const
     // (a bounded probe sequence: a table this full is reported as overflow, not searched on)
     for (u64 probe = 0; probe <= mask && probe < 4096; ++probe, pos = (pos + 1) & mask) {
         BsiSlot *s = table + pos;
-        u32 f = *((volatile u32 *)&s->flag);
+        u32 f = bsi_ld_acquire_u32(&s->flag);
         if (f == 0u) {
             u32 old = atomicCAS(&s->flag, 0u, 1u);
             if (old == 0u) {
@@ -236,8 +249,7 @@ __device__ __noinline__ void bsi_table_add(BsiSlot *table, u32 log2_slots, const
                 f = old;
             }
         }
-        while (f == 1u) f = *((volatile u32 *)&s->flag);
-        __threadfence();
+        while (f != 2u) f = bsi_ld_acquire_u32(&s->flag);
         bool same = true;
 #pragma unroll
         for (int i = 0; i < BSI_KW; ++i) same = same && (((volatile u64 *)s->key)[i] == key[i]);
@@ -443,6 +455,7 @@ __device__ __forceinline__ u64 bsi_grab_word(u64 *counter) {
 // warp-aggregated reservation of `n` queue entries per thread; returns this thread's first index
 __device__ __forceinline__ u64 bsi_reserve(u64 *counter, u32 n) {
     const u32 lane = threadIdx.x & 31u;
+    if (!__any_sync(0xFFFFFFFFu, n != 0u)) return 0ull;      // (the usual case for two of the three queues)
     u32 incl = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1486,8 +1499,13 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 //   groups  lanes with equal keys, found by broadcasting one lane's key bits against all lanes
 //           (2 ops per node and group; the ordered regime has a handful of groups per word);
 //   mu      the lock-step of x_j (from the index word) and P(j); the lanes that agree first at
-//           step j add (count, count * j, count * j^2) to their groups -- one popc per group.
+//           step j add (1, j, j^2) to their groups.
 // Only then the table is touched, once per group.
+#if BSI_TUNE & 8
+#define BSI_EW_DICT_MIN_LAM BSI_DICT_MIN_LAM
+#else
+#define BSI_EW_DICT_MIN_LAM BSI_EARLY_DICT_MIN_LAM
+#endif
 struct BsiGroups {
     u32 n_groups;
     u32 mask[32];               // lanes of the group
@@ -1498,27 +1516,33 @@ struct BsiGroups {
     u32 n[32], late[32];        // lanes that close in time / only after max_t
     u32 s1[32];                 // sum of j over the former (j < 2^24, at most 32 lanes)
     u64 s2[32];                 // sum of j^2
+    unsigned char gid[32];      // lane -> its group
 };
 __device__ __forceinline__ void bsi_group_open(BsiGroups &gr, u32 g, u32 mask, u32 lam, u64 T) {
     gr.mask[g] = mask;
     gr.lam[g] = lam;
     gr.jlim[g] = (u64)lam <= T ? T - lam + 1ull : 0ull;
     gr.n[g] = 0u; gr.late[g] = 0u; gr.s1[g] = 0u; gr.s2[g] = 0ull;
+    while (mask) {
+        const u32 l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        gr.gid[l] = (unsigned char)g;
+    }
 }
 
-// lanes m reached their cycle at relative time j: one popc per group
+// lanes m reached their cycle at relative time j (the lanes of a word reach theirs at up to 32
+// different times, mostly one or two lanes at a time: per lane, not per group)
 __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
-#pragma unroll 1
-    for (u32 g = 0; g < gr.n_groups; ++g) {
-        const u32 cnt = __popc(m & gr.mask[g]);
-        if (!cnt) continue;
+    while (m) {
+        const u32 l = __ffs(m) - 1;
+        m &= m - 1;
+        const u32 g = gr.gid[l];
         if ((u64)j < gr.jlim[g]) {
-            const u32 cj = cnt * j;
-            gr.n[g] += cnt;
-            gr.s1[g] += cj;
-            gr.s2[g] += (u64)cj * j;
+            gr.n[g] += 1u;
+            gr.s1[g] += j;
+            gr.s2[g] += (u64)j * j;
         } else {
-            gr.late[g] += cnt;
+            gr.late[g] += 1u;
         }
     }
 }
@@ -1529,14 +1553,24 @@ __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
 // attractors: consecutive words of a thread hit the same few keys, so a group costs a key compare
 // and three additions instead of a table probe and three atomics on one of a few hot L2 addresses
 // (or the warp-wide aggregation that kept those atomics apart before).
-#define BSI_TC_WAYS 4
+// (16 entries: with 4, the 39 attractors of cambium2 -- five groups per word -- and the 7 of the
+//  seed-1 network evicted on most words, and the evictions' atomics queued up on the same few slots:
+//  47 % of the kernel's stall samples sat in bsi_table_add.  The victim is the entry with the fewest
+//  lanes: an attractor that takes most of the lanes is never written before the end.)
+#if BSI_TUNE & 2
+#define BSI_TC_WAYS 8
+#elif BSI_TUNE & 4
+#define BSI_TC_WAYS 32
+#else
+#define BSI_TC_WAYS 16
+#endif
 struct BsiTCache {
     u64 key[BSI_TC_WAYS][BSI_KW];
     u64 n[BSI_TC_WAYS], s1[BSI_TC_WAYS], s2[BSI_TC_WAYS];
     u32 lam[BSI_TC_WAYS];
-    u32 used, victim;
+    u32 used;
 };
-__device__ __forceinline__ void bsi_tcache_init(BsiTCache &tc) { tc.used = 0u; tc.victim = 0u; }
+__device__ __forceinline__ void bsi_tcache_init(BsiTCache &tc) { tc.used = 0u; }
 __device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n, u64 s1, u64 s2, u32 lam,
                                             BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
 #pragma unroll 1
@@ -1553,8 +1587,14 @@ __device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n
     if (i < BSI_TC_WAYS) {
         tc.used = i + 1u;
     } else {
-        i = tc.victim;
-        tc.victim = (i + 1u) % BSI_TC_WAYS;
+        i = 0u;
+#pragma unroll 1
+        for (u32 q = 1; q < BSI_TC_WAYS; ++q)
+            if (tc.n[q] < tc.n[i]) i = q;
+        if (n <= tc.n[i]) {                              // (the newcomer is the smallest: it goes itself)
+            bsi_table_add(table, log2_slots, key, n, s1, s2, lam, ctr);
+            return;
+        }
         bsi_table_add(table, log2_slots, tc.key[i], tc.n[i], tc.s1[i], tc.s2[i], tc.lam[i], ctr);
     }
 #pragma unroll
@@ -1673,7 +1713,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
         }
         u32 pb_[BSI_N];                                  // P(0), bit-sliced (cycles only)
         bool via_dict = false;
-        if (lam_max > BSI_EARLY_DICT_MIN_LAM && dict.slots) {
+        if (lam_max > BSI_EW_DICT_MIN_LAM && dict.slots) {
             via_dict = bsi_early_dict(dict, ent.y, valid, n_ev, evm, evl, eva, pb_, gr, T);
             if (via_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) }
         }
@@ -1745,7 +1785,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
                 u32 lam0 = 1u;
 #pragma unroll 1
                 for (u32 k = 0; k < n_ev; ++k)
-                    if ((evm[k] >> l0) & 1u) lam0 = evl[k];
+                    if ((evm[k] >> l0) & 1u) { lam0 = evl[k]; break; }
                 bsi_group_open(gr, G, g, lam0, T);
 #pragma unroll
                 for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = (u64)kc_[2 * i] | ((u64)kc_[2 * i + 1] << 32);
@@ -1753,7 +1793,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
             }
             gr.n_groups = G;
             // the walked cycles go into the dictionary (once per attractor: the claim decides)
-            if (learn && dict.slots && lam_max > BSI_EARLY_DICT_MIN_LAM) {
+            if (learn && dict.slots && lam_max > BSI_EW_DICT_MIN_LAM) {
 #pragma unroll 1
                 for (u32 g = 0; g < G; ++g) {
                     u32 base, slot;
@@ -1867,6 +1907,36 @@ bsi_resolve_mu(BsiFound *found_q, const u64 *n_found_p, u64 few_words, u64 T, u6
     if (n_rej) atomicAdd(&ctr->n_without, n_rej);
 }
 
+#endif  // BSI_UNIT != 5
+#if BSI_UNIT == 0 || BSI_UNIT == 6
+// The early-word queue of a dense round: keys, mu and aggregation of the lanes that matched an early
+// checkpoint, straight from the word's bit-sliced state (see bsi_early_word).
+extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
+bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u64 *n_found_p,
+                  u64 few_words, u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
+                  u32 log2_slots, BsiCounters *ctr, const BsiDict dict) {
+    const u64 n_early = *n_early_p;
+    if (n_early == 0) return;
+    if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
+    const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
+    u64 steps = 0, n_acc = 0, n_rej = 0;
+    BsiTCache tc;
+    bsi_tcache_init(tc);
+    for (;;) {
+        const u64 e = bsi_grab_word(&ctr->next_word4);
+        if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
+        if (e < n_early)
+            bsi_early_word(eq, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict, true, tc, steps,
+                           n_acc, n_rej);
+    }
+    __syncwarp();
+    bsi_tcache_flush<true>(tc, table, log2_slots, ctr);
+    if (steps) atomicAdd(&ctr->steps, steps);
+    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
+    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
+}
+#endif  // BSI_UNIT 6
+#if BSI_UNIT != 3 && BSI_UNIT != 6
 // Orbits on request (reference attract.py:22-25: the states of an aggregated attractor, key state
 // first): thread i finds keys[i] in the cycle dictionary or stores its orbit there -- the same fast
 // walk the resolution kernels use (32 phases of the orbit per step) -- and reports where it starts
@@ -1906,36 +1976,6 @@ extern "C" __global__ void bsi_dict_learn_keys(const u64 *keys, const u64 *lams,
     }
 }
 
-#endif  // BSI_UNIT != 5
-#if BSI_UNIT == 0 || BSI_UNIT == 6
-// The early-word queue of a dense round: keys, mu and aggregation of the lanes that matched an early
-// checkpoint, straight from the word's bit-sliced state (see bsi_early_word).
-extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
-bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u64 *n_found_p,
-                  u64 few_words, u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table,
-                  u32 log2_slots, BsiCounters *ctr, const BsiDict dict) {
-    const u64 n_early = *n_early_p;
-    if (n_early == 0) return;
-    if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
-    const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
-    u64 steps = 0, n_acc = 0, n_rej = 0;
-    BsiTCache tc;
-    bsi_tcache_init(tc);
-    for (;;) {
-        const u64 e = bsi_grab_word(&ctr->next_word4);
-        if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
-        if (e < n_early)
-            bsi_early_word(eq, e, T, max_attractor_l, stop_t_cap, table, log2_slots, ctr, dict, true, tc, steps,
-                           n_acc, n_rej);
-    }
-    __syncwarp();
-    bsi_tcache_flush<true>(tc, table, log2_slots, ctr);
-    if (steps) atomicAdd(&ctr->steps, steps);
-    if (n_acc) atomicAdd(&ctr->n_accepted, n_acc);
-    if (n_rej) atomicAdd(&ctr->n_without, n_rej);
-}
-#endif  // BSI_UNIT 6
-#if BSI_UNIT != 3 && BSI_UNIT != 6
 extern "C" __global__ void __launch_bounds__(BSI_BLOCK)
 bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_base, u64 early_cap,
             u64 T, u64 max_attractor_l, u64 stop_t_cap, BsiSlot *table, u32 log2_slots,

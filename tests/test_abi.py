@@ -88,7 +88,7 @@ def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
     script = (
         "import sys, time, hashlib; sys.path.insert(0, %r)\n"
         "from boolsi_b200 import _lib, synth\n"
-        "cfg = synth.random_attract_problem(24, 3, 5, n_free=10)\n"
+        "cfg = synth.random_attract_problem(24, 3, 5, n_free=22)\n"
         "pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],\n"
         "                        cfg['origin simulation problem'], cfg['simulation problem variations'])\n"
         "t = time.perf_counter()\n"
@@ -104,6 +104,8 @@ def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
 
     cold = run(tmp_path)
     files = sorted(os.listdir(tmp_path))
+    # (2^22 initial states: every kernel unit; a small problem space would leave the queue kernel and
+    #  the throughput-mode resolution kernels to the first run that needs them)
     assert len(files) == 6 and all(f.startswith('bsi-') and f.endswith('.cubin') for f in files), files
     warm = run(tmp_path)
     assert warm[1:] == cold[1:]
@@ -117,3 +119,26 @@ def test_disk_cache_hands_the_next_process_identical_cubins(tmp_path):
     assert again[1:] == cold[1:]
     assert open(victim, 'rb').read() == data                      # rewritten after the recompile
     assert run(None)[1:] == cold[1:]                              # and with the disk level off: plain NVRTC
+
+
+def test_small_problem_spaces_leave_three_kernel_units_for_later(tmp_path):
+    """A problem space whose queues can never be long (here 2^10 initial states) is specialised for the
+    dense trajectory kernel, the latency-oriented resolution kernels and the rest only: half the cold
+    start of a job that consists of little else.  The other units are compiled by the first run that
+    needs them (GPU tests: retry rounds and forced throughput mode on small spaces)."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from boolsi_b200 import _lib, synth\n"
+        "cfg = synth.random_attract_problem(24, 3, 5, n_free=10)\n"
+        "pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],\n"
+        "                        cfg['origin simulation problem'], cfg['simulation problem variations'])\n"
+        "plan = _lib.Plan(pk, _lib.MODE_ATTRACT, offline=True)\n" % repo)
+    env = dict(os.environ)
+    env['BSI_CACHE_DIR'] = str(tmp_path)
+    subprocess.run([sys.executable, '-c', script], env=env, check=True)
+    files = sorted(os.listdir(tmp_path))
+    assert sorted(f[-8:-6] for f in files) == ['u1', 'u4', 'u5'], files
