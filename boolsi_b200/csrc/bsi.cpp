@@ -603,12 +603,14 @@ int compile_plan(bsi_plan *p) {
     // cycle, 32 lookups + gathers + the 32x32 transposes about 2800 instructions.
     const int walk_per_step = 2 * std::max(1, p->m.n) + 4 * p->m.n;      // (U <= N for K <= 3; a bound is enough)
     const int dict_min_lam = std::max(8, 2800 / walk_per_step);
-    // Early words get keys AND P(0) out of ONE walk of max lambda - 1 steps, each an update plus the
-    // bit-sliced minimum (about U + 2 N + 10 instructions), while their way through the dictionary --
-    // transposes to state codes, per-lane lookups and gathers, transposes back -- costs about 8000
-    // (measured on cambium2, where the 18-cycle sat just above the old common threshold: the 6 % of
-    // the words that held one took 12 % of the kernel's instructions).
-    const int early_dict_min_lam = std::max(8, 8000 / (3 * p->m.n + 10));
+    // Early words get keys AND P(0) out of ONE walk of max lambda - 1 steps, each an update, the
+    // bit-sliced minimum and its select (about 4 N + 15 instructions, a long dependent chain), while
+    // their way through the dictionary -- transposes to state codes, per-lane lookups and gathers,
+    // transposes back -- costs about 2600 + 55 N instructions of memory latency that overlaps.
+    // Measured on both sides of the line: cambium2 (N = 30, threshold 31) walks its 18-cycle -- the
+    // dictionary cost the 6 % of its words that hold one 12 % of the kernel -- and the seed-1 network
+    // (N = 64, threshold 22) looks its 29- and 58-cycles up (walking them: 8.6 instead of 5.5 ms).
+    const int early_dict_min_lam = std::max(8, (2600 + 55 * p->m.n) / (4 * p->m.n + 15));
     p->smem_slots = p->opts.smem_slots ? (int)p->opts.smem_slots : 3;
     if (p->smem_slots < 1 || p->smem_slots > 3) return fail(BSI_E_ARG, "smem_slots must be 1, 2 or 3");
     const std::string header = bsi::generate_header(p->m, filter, filter2, p->block, min_blocks, (int)p->opts.debug_stats, p->info) +

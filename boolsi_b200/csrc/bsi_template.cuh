@@ -1530,19 +1530,36 @@ __device__ __forceinline__ void bsi_group_open(BsiGroups &gr, u32 g, u32 mask, u
     }
 }
 
-// lanes m reached their cycle at relative time j (the lanes of a word reach theirs at up to 32
-// different times, mostly one or two lanes at a time: per lane, not per group)
+// lanes m reached their cycle at relative time j.  Two regimes: whole words that close together (the
+// ordered regime: a few events of many lanes each) are counted per GROUP, one popc each; lanes that
+// close one by one (up to 32 events per word, several groups) per LANE through its group number.
 __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
-    while (m) {
-        const u32 l = __ffs(m) - 1;
-        m &= m - 1;
-        const u32 g = gr.gid[l];
+    if ((u32)__popc(m) < gr.n_groups) {
+        while (m) {
+            const u32 l = __ffs(m) - 1;
+            m &= m - 1;
+            const u32 g = gr.gid[l];
+            if ((u64)j < gr.jlim[g]) {
+                gr.n[g] += 1u;
+                gr.s1[g] += j;
+                gr.s2[g] += (u64)j * j;
+            } else {
+                gr.late[g] += 1u;
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (u32 g = 0; g < gr.n_groups; ++g) {
+        const u32 cnt = __popc(m & gr.mask[g]);
+        if (!cnt) continue;
         if ((u64)j < gr.jlim[g]) {
-            gr.n[g] += 1u;
-            gr.s1[g] += j;
-            gr.s2[g] += (u64)j * j;
+            const u32 cj = cnt * j;
+            gr.n[g] += cnt;
+            gr.s1[g] += cj;
+            gr.s2[g] += (u64)cj * j;
         } else {
-            gr.late[g] += 1u;
+            gr.late[g] += cnt;
         }
     }
 }
@@ -1579,7 +1596,18 @@ __device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n
 #pragma unroll
         for (int k = 0; k < BSI_KW; ++k) same = same && tc.key[i][k] == key[k];
         if (same) {
-            tc.n[i] += n; tc.s1[i] += s1; tc.s2[i] += s2;
+            const u64 nn = tc.n[i] + n;
+            tc.n[i] = nn; tc.s1[i] += s1; tc.s2[i] += s2;
+            // (kept in the order of their counts: the attractors that take most of the lanes are found
+            //  by the first compare or two; entries swap only when their counts cross)
+            if (i && nn > tc.n[i - 1u]) {
+#pragma unroll
+                for (int k = 0; k < BSI_KW; ++k) { const u64 t = tc.key[i][k]; tc.key[i][k] = tc.key[i - 1u][k]; tc.key[i - 1u][k] = t; }
+                u64 t = tc.n[i]; tc.n[i] = tc.n[i - 1u]; tc.n[i - 1u] = t;
+                t = tc.s1[i]; tc.s1[i] = tc.s1[i - 1u]; tc.s1[i - 1u] = t;
+                t = tc.s2[i]; tc.s2[i] = tc.s2[i - 1u]; tc.s2[i - 1u] = t;
+                const u32 tl = tc.lam[i]; tc.lam[i] = tc.lam[i - 1u]; tc.lam[i - 1u] = tl;
+            }
             return;
         }
     }
