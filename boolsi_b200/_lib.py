@@ -28,7 +28,7 @@ EXPORTS = [
     'bsi_abi_version', 'bsi_last_error', 'bsi_device_count', 'bsi_plan_create',
     'bsi_plan_create_offline', 'bsi_plan_destroy', 'bsi_plan_n_problems', 'bsi_plan_key_words',
     'bsi_plan_set_stream', 'bsi_plan_source', 'bsi_plan_build_log', 'bsi_plan_cubin',
-    'bsi_plan_launch_config', 'bsi_plan_op_counts', 'bsi_compile_only', 'bsi_attract_run',
+    'bsi_plan_launch_config', 'bsi_plan_op_counts', 'bsi_plan_update_quiet_lop3', 'bsi_compile_only', 'bsi_attract_run',
     'bsi_attract_table_clear', 'bsi_attract_table_count', 'bsi_attract_table_read',
     'bsi_attract_table_export_device', 'bsi_attract_table_merge_device', 'bsi_attractor_states',
     'bsi_simulate_run', 'bsi_simulate_list', 'bsi_target_run', 'bsi_measure_lop3_peak',
@@ -124,6 +124,7 @@ def lib():
         L.bsi_plan_cubin.argtypes = [p, C.POINTER(p), C.POINTER(u64)]
         L.bsi_plan_launch_config.argtypes = [p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.bsi_plan_op_counts.argtypes = [p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.bsi_plan_update_quiet_lop3.argtypes = [p]
         L.bsi_compile_only.argtypes = [C.POINTER(NetworkDesc), C.POINTER(SpaceDesc), i,
                                        C.POINTER(TargetDesc), C.POINTER(PlanOpts),
                                        C.POINTER(u64), C.c_char_p, u64]
@@ -356,7 +357,14 @@ class Plan:
     def op_counts(self):
         u, c, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
         check(lib().bsi_plan_op_counts(self._h, C.byref(u), C.byref(c), C.byref(f)))
-        return {'update_lop3': u.value, 'compare_lop3': c.value, 'filter_lop3': f.value}
+        return {'update_lop3': u.value, 'compare_lop3': c.value, 'filter_lop3': f.value,
+                'update_quiet_lop3': self._quiet_lop3()}
+
+    def _quiet_lop3(self):
+        v = lib().bsi_plan_update_quiet_lop3(self._h)
+        if v < 0:
+            check(v)
+        return v
 
     def launch_config(self):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()

@@ -954,6 +954,11 @@ int bsi_plan_op_counts(const bsi_plan *p, uint32_t *update_lop3, uint32_t *compa
     return BSI_OK;
 }
 
+int bsi_plan_update_quiet_lop3(const bsi_plan *p) {
+    if (!p) return fail(BSI_E_ARG, "null plan");
+    return p->info.update_quiet_lop3;
+}
+
 int bsi_plan_launch_config(const bsi_plan *p, uint32_t *n_sms, uint32_t *block_threads,
                            uint32_t *blocks_per_sm) {
     if (!p) return fail(BSI_E_ARG, "null plan");

@@ -313,6 +313,7 @@ inline std::string load_model(const bsi_network_desc *net, const bsi_space_desc 
 struct GenInfo {
     int filter2_nodes = 0;   // stage-2 filter words per checkpoint slot (shared memory)
     int update_lop3 = 0;     // LOP3 per word-step of the autonomous update
+    int update_quiet_lop3 = 0;   // the same past the last perturbation time (fixed nodes folded into their readers)
     int compare_lop3 = 0;    // full compare
     int filter_lop3 = 0;     // cheap pre-compare
     std::vector<int> filter_nodes;
@@ -413,6 +414,33 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         }
         o << "#define BSI_UPDATE(D, S) { " << syn.temp_decls() << syn.body() << "}\n";
         info.update_lop3 = syn.n_lop3();
+
+        // The same update for a state that is known to carry its fixed values: a node fixed for all lanes
+        // holds its constant from time 1 on unless a perturbation has just overwritten it (model.py:31-49,
+        // 66-71), so past the last perturbation time the readers of such a node can take the constant
+        // instead of the register -- one input fewer per reader, and the node's word leaves the loop.
+        Lop3Synth quiet("S");
+        for (int i : order) {
+            std::string dst = "D##" + std::to_string(i);
+            auto fx = m.fixed.find(i);
+            bool varfix = fixvar_nodes.count(i) > 0;
+            if (fx != m.fixed.end() && !varfix) {
+                Operand c; c.kind = Operand::CONST; c.value = fx->second;
+                quiet.assign(dst, c);
+                continue;
+            }
+            BoolFn f = m.fn[i];
+            for (int q = 0; q < f.k();) {
+                auto src = m.fixed.find(f.vars[q]);
+                if (src != m.fixed.end() && !fixvar_nodes.count(f.vars[q])) f = f.cofactor(q, src->second);
+                else ++q;
+            }
+            Operand v = quiet.synth(f);
+            if (varfix) quiet.assign_masked(dst, v, "fm" + std::to_string(i), "fv" + std::to_string(i));
+            else quiet.assign(dst, v);
+        }
+        o << "#define BSI_UPDATE_QUIET(D, S) { " << quiet.temp_decls() << quiet.body() << "}\n";
+        info.update_quiet_lop3 = quiet.n_lop3();
     }
 
     // ---- perturbations scheduled at time t (model.py:70-71), uniform part + per-lane part ----
@@ -507,10 +535,19 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
     // target compare: acc |= (X ^ code) on the constrained nodes
     if (m.mode == BSI_MODE_TARGET) {
         o << "#define BSI_CMP_TARGET(acc, X) {";
-        for (int node : m.target_nodes) {
-            int bit = (int)((m.target.code[node >> 6] >> (node & 63)) & 1);
-            // acc |= X ^ const  ->  acc | ~X  (want 1) or acc | X (want 0)
-            o << " acc |= " << (bit ? "~" : "") << "X##" << node << ";";
+        // acc |= X ^ code bit: two constrained nodes per lop3, acc | (b ^ cb) | (c ^ cc)
+        auto want = [&](int node) { return (int)((m.target.code[node >> 6] >> (node & 63)) & 1); };
+        size_t q = 0;
+        for (; q + 1 < m.target_nodes.size(); q += 2) {
+            int nb = m.target_nodes[q], nc = m.target_nodes[q + 1];
+            unsigned lut = 0;
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c)
+                if (a | (b ^ want(nb)) | (c ^ want(nc))) lut |= 1u << (a << 2 | b << 1 | c);
+            o << " acc = bsi_lop3<0x" << std::hex << lut << std::dec << ">(acc, X##" << nb << ", X##" << nc << ");";
+        }
+        if (q < m.target_nodes.size()) {
+            int node = m.target_nodes[q];
+            o << " acc |= " << (want(node) ? "~" : "") << "X##" << node << ";";
         }
         o << " }\n";
     }

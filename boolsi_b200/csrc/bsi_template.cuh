@@ -2350,20 +2350,61 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
             }                                                                     \
         }                                                                         \
     }
-        // two steps per iteration (a -> b -> a), so that no step needs a register copy
+        // two steps per iteration (a -> b -> a), so that no step needs a register copy.
+        // General steps (perturbation switch, per-lane start times, 64-bit clock) are only needed up to the
+        // last perturbation time of any lane; from there on pass 0 runs a tight loop -- update, target
+        // compare, a 32-bit countdown -- in which every lane is started and nothing is perturbed.
         bool stop_ = false, cur_is_b = false;
-        for (u64 t = 0;; t += 2) {
+        const u64 lp_max_ = BSI_LP_MAX;
+        const u64 gen_end = (pass == 0 && T > lp_max_ && T - lp_max_ < 0xFFFFFFF0ull) ? lp_max_ : ~0ull;
+        u64 t = 0;
+        for (; t <= gen_end; t += 2) {
             BSI_TCHECK(a, t)
             if (stop_) { cur_is_b = false; break; }
             BSI_UPDATE(b, a)
             BSI_PERTURB(b, (t + 1))
-            ++dev_steps;
             BSI_TCHECK(b, t + 1)
-            if (stop_) { cur_is_b = true; break; }
+            if (stop_) { cur_is_b = true; ++t; break; }
             BSI_UPDATE(a, b)
             BSI_PERTURB(a, (t + 2))
-            ++dev_steps;
         }
+        if (!stop_) {
+            // here: pass 0, state a at time t (not yet tested), lp_max < t <= T, every valid lane started
+            u32 left = (u32)(T - t);            // updates until the horizon
+            const u32 t0 = (u32)t;              // (finite target times are below 2^32: bsi_target_run)
+            u32 k = 0;                          // updates done in this loop
+#define BSI_TFAST(X)                                                              \
+    {                                                                             \
+        u32 acc = ~alive;                                                         \
+        BSI_CMP_TARGET(acc, X)                                                    \
+        u32 m_ = ~acc;                                                            \
+        if (m_) {                                                                 \
+            alive &= ~m_;                                                         \
+            while (m_) {                                                          \
+                u32 l_ = __ffs(m_) - 1;                                           \
+                m_ &= m_ - 1;                                                     \
+                th_s[l_ * BSI_BLOCK + threadIdx.x] = t0 + k;                      \
+            }                                                                     \
+            if (!alive) break;                                                    \
+        }                                                                         \
+    }
+            for (;;) {
+                cur_is_b = false;
+                BSI_TFAST(a)
+                if (k == left) break;
+                BSI_UPDATE_QUIET(b, a)
+                ++k;
+                cur_is_b = true;
+                BSI_TFAST(b)
+                if (k == left) break;
+                BSI_UPDATE_QUIET(a, b)
+                ++k;
+            }
+#undef BSI_TFAST
+            hit = valid & ~alive;               // (pass 0: lanes leave `alive` only by hitting)
+            t += k;
+        }
+        dev_steps += t;
 #undef BSI_TCHECK
         if (pass == 0) {
             if (!check_closure || !alive) break;

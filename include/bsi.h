@@ -217,6 +217,10 @@ int bsi_plan_launch_config(const bsi_plan *plan, uint32_t *n_sms, uint32_t *bloc
 /* Static cost model of the specialised step: LOP3 per 32-lane word-step (update, compare). */
 int bsi_plan_op_counts(const bsi_plan *plan, uint32_t *update_lop3, uint32_t *compare_lop3,
                        uint32_t *filter_lop3);
+/* LOP3 per word-step of the update past the last perturbation time, where nodes fixed for every lane
+ * are folded into their readers as constants (model.py:31-49); equals update_lop3 without fixed nodes.
+ * Negative = error code. */
+int bsi_plan_update_quiet_lop3(const bsi_plan *plan);
 
 /*
  * Specialise a plan's kernels WITHOUT a device (NVRTC only): used by the build check and the CPU

@@ -7,6 +7,7 @@
 //
 // stdin:  commands, one per line
 //   U  a_0 .. a_{N-1}                 -> BSI_UPDATE(b, a): prints b_0 .. b_{N-1}
+//   Q  a_0 .. a_{N-1}                 -> BSI_UPDATE_QUIET(b, a) (fixed nodes folded into their readers)
 //   P  t  a_0 .. a_{N-1}              -> BSI_PERTURB(a, t): prints a_0 .. a_{N-1}
 //   D  W                              -> BSI_INIT_DENSE(a, W): prints a_0 .. a_{N-1}
 //   L  idx                            -> BSI_LANE_SETUP(0, idx, c): prints c[0..KW)
@@ -64,6 +65,10 @@ int main() {
         if (cmd == 'U') {
             BSI_FOR_NODES(READ_A)
             BSI_UPDATE(b, a)
+            BSI_FOR_NODES(PRINT_B)
+        } else if (cmd == 'Q') {
+            BSI_FOR_NODES(READ_A)
+            BSI_UPDATE_QUIET(b, a)
             BSI_FOR_NODES(PRINT_B)
         } else if (cmd == 'P') {
             u64 t = 0;

@@ -86,6 +86,20 @@ def test_generated_macros_executed_on_the_host(seed, tmp_path):
             nxt.append(new)
         cmds.append('U ' + ' '.join(map(str, a)))
         want.append(_words(nxt, n))
+    # ---- BSI_UPDATE_QUIET: the same step from states that hold their fixed values (any time >= 1 that is
+    #      not a perturbation time): fixed nodes enter their readers as constants ------------------
+    for _ in range(6):
+        a = [int(x) for x in rng.integers(0, 2 ** 32, size=n)]
+        for node, value in fixed.items():
+            a[node] = 0xFFFFFFFF if value else 0
+        nxt = []
+        for state in _lanes(a, n):
+            new = [tts[i][tuple(state[p] for p in preds[i])] for i in range(n)]
+            for node, value in fixed.items():
+                new[node] = value
+            nxt.append(new)
+        cmds.append('Q ' + ' '.join(map(str, a)))
+        want.append(_words(nxt, n))
     # ---- BSI_PERTURB: overrides at their times (model.py:70-71) -----------------------------------
     for t in range(0, 10):
         a = [int(x) for x in rng.integers(0, 2 ** 32, size=n)]
