@@ -70,7 +70,7 @@ class PlanOpts(C.Structure):
                 ('min_blocks', C.c_uint32), ('debug_stats', C.c_uint32),
                 ('resolve_few_words', C.c_uint32), ('no_early_words', C.c_uint32),
                 ('smem_slots', C.c_uint32), ('source_only', C.c_uint32), ('keep_dict', C.c_uint32),
-                ('tune', C.c_uint32), ('reserved', C.c_uint32 * 2)]
+                ('tune', C.c_uint32), ('target_hit_list', C.c_uint32), ('reserved', C.c_uint32 * 1)]
 
 
 class RunStats(C.Structure):

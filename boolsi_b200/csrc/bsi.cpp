@@ -1616,7 +1616,70 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
     uint64_t written = 0, total_hits = 0;
     std::vector<std::pair<uint64_t, uint64_t>> hits;
     std::vector<uint64_t> hi, ht;
-    for (uint64_t b = idx_begin; b < idx_end;) {
+    auto fetch_hits = [&](uint64_t n) -> int {
+        hi.resize(n);
+        ht.resize(n);
+        CU_CHECK(cuMemcpyDtoHAsync(hi.data(), p->misc.p, 8 * n, p->stream));
+        CU_CHECK(cuMemcpyDtoHAsync(ht.data(), p->misc2.p, 8 * n, p->stream));
+        CU_CHECK(cuStreamSynchronize(p->stream));
+        for (uint64_t i = 0; i < n; ++i) hits.push_back({hi[i], ht[i]});
+        return BSI_OK;
+    };
+    auto emit_sorted = [&]() {
+        std::sort(hits.begin(), hits.end());
+        total_hits += hits.size();
+        for (auto &h : hits) {
+            if (written >= cap) break;
+            hit_index[written] = h.first;
+            hit_t[written] = h.second;
+            ++written;
+        }
+    };
+    // A finite max_t needs one round per chunk and no decision of the host between them: all chunks are
+    // enqueued back to back, their hits appended to ONE list (the kernel's counter runs on), and the
+    // host reads it once -- the GPU does not wait for the host between chunks.  The list holds 2^24
+    // hits; a job with more falls back to the chunk-by-chunk form below.
+    bool done = false;
+    const uint64_t kOnePassHits = p->opts.target_hit_list ? p->opts.target_hit_list : (uint64_t)1 << 24;
+    if (max_t != BSI_INF && p->opts.target_hit_list != 1) {
+        const uint64_t total = idx_end - idx_begin;
+        uint64_t hit_cap = std::min(total, kOnePassHits);
+        if ((rc = ensure(p, p->misc, 8 * std::max<uint64_t>(hit_cap, 1))) ||
+            (rc = ensure(p, p->misc2, 8 * std::max<uint64_t>(hit_cap, 1)))) return rc;
+        uint64_t T = max_t;
+        int check_closure = 0, n_chunks = 0;
+        CUdeviceptr none = 0;
+        for (uint64_t b = idx_begin; b < idx_end;) {
+            uint64_t e = std::min(idx_end, b + chunk);
+            uint64_t n_in = e - b;
+            CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, kPerRoundBytes, p->stream));
+            void *args[] = {&b, &none, &n_in, &T, &check_closure, &p->misc.p, &p->misc2.p, &hit_cap,
+                            &none, &none, &p->ctr.p};
+            uint64_t n_words = (n_in + 31) >> 5;
+            if ((rc = launch(p, p->f_target, (unsigned)((n_words + p->block - 1) / p->block), p->block, 0, args))) return rc;
+            ++st.rounds;
+            b = e;
+            // (a progress hook wants to hear from a long run: wait for the device every 16 chunks)
+            if (p->progress && (++n_chunks % 16 == 0 || b == idx_end)) {
+                CU_CHECK(cuStreamSynchronize(p->stream));
+                p->progress(b - idx_begin, idx_end - idx_begin, p->progress_user);
+            }
+        }
+        CU_CHECK(cuEventRecord(e1, p->stream));
+        Counters c;
+        if ((rc = read_counters(p, &c))) return rc;
+        if (c.n_hits <= hit_cap) {
+            if (c.n_hits && (rc = fetch_hits(c.n_hits))) return rc;
+            emit_sorted();
+            done = true;
+        } else {
+            // (start over: the counters of the attempt are dropped)
+            CU_CHECK(cuMemsetD8Async(p->ctr.p, 0, sizeof(Counters), p->stream));
+            CU_CHECK(cuEventRecord(e0, p->stream));
+            st.rounds = 0;
+        }
+    }
+    for (uint64_t b = idx_begin; !done && b < idx_end;) {
         uint64_t e = std::min(idx_end, b + chunk);
         uint64_t n_lanes = e - b;
         if ((rc = ensure(p, p->misc, 8 * n_lanes)) || (rc = ensure(p, p->misc2, 8 * n_lanes))) return rc;
@@ -1644,14 +1707,7 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
             ++st.rounds;
             Counters c;
             if ((rc = read_counters(p, &c))) return rc;
-            if (c.n_hits) {
-                hi.resize(c.n_hits);
-                ht.resize(c.n_hits);
-                CU_CHECK(cuMemcpyDtoHAsync(hi.data(), p->misc.p, 8 * c.n_hits, p->stream));
-                CU_CHECK(cuMemcpyDtoHAsync(ht.data(), p->misc2.p, 8 * c.n_hits, p->stream));
-                CU_CHECK(cuStreamSynchronize(p->stream));
-                for (uint64_t i = 0; i < c.n_hits; ++i) hits.push_back({hi[i], ht[i]});
-            }
+            if (c.n_hits && (rc = fetch_hits(c.n_hits))) return rc;
             st.n_without += c.n_found;     // closed without a hit
             if (!check_closure || c.n_retry == 0) break;
             if (T >= kMaxH) return fail(BSI_E_UNSUPPORTED, "a trajectory did not close within 2^30 steps");
@@ -1661,18 +1717,11 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
             T = std::min(T * 4, kMaxH);
             if (max_t != BSI_INF && T > max_t) T = max_t;
         }
-        std::sort(hits.begin(), hits.end());
-        total_hits += hits.size();
-        for (auto &h : hits) {
-            if (written >= cap) break;
-            hit_index[written] = h.first;
-            hit_t[written] = h.second;
-            ++written;
-        }
+        emit_sorted();
         b = e;
         if (p->progress) p->progress(b - idx_begin, idx_end - idx_begin, p->progress_user);
     }
-    CU_CHECK(cuEventRecord(e1, p->stream));
+    if (!done) CU_CHECK(cuEventRecord(e1, p->stream));
     Counters c;
     if ((rc = read_counters(p, &c))) return rc;
     CU_CHECK(cuEventSynchronize(e1));

@@ -132,7 +132,10 @@ typedef struct bsi_plan_opts {
     uint32_t keep_dict;        /* attract: 1 = bsi_attract_table_clear leaves the cycle dictionary as it is (it
                                   holds facts about the network's dynamics, not results) */
     uint32_t tune;             /* experiment switches of the kernel template (BSI_TUNE), 0 = the shipped variant */
-    uint32_t reserved[2];
+    uint32_t target_hit_list;  /* target with a finite max_t: capacity of the hit list that all chunks of a run
+                                  append to without a host round trip between them; 0 = auto (2^24 hits), 1 = off
+                                  (chunk by chunk, what a run with more hits than the list holds falls back to) */
+    uint32_t reserved[1];
 } bsi_plan_opts;
 
 /* One aggregated attractor: the replacement for AggregatedAttractor (reference attract.py:18-45). */

@@ -191,6 +191,34 @@ def test_target_vs_c_oracle_config5_shape():
         assert [int(t) for t in hit_t] == [int(rec['stop_t'][i]) for i in want]
 
 
+@pytest.mark.parametrize('opts', [dict(target_hit_list=1), dict(target_hit_list=7), dict(chunk_log2=9)],
+                         ids=['chunk-by-chunk', 'hit-list-overflow', 'one-pass-many-chunks'])
+def test_target_run_forms_agree(opts):
+    """A finite max_t runs all chunks back to back into one hit list; chunk by chunk (the form of
+    max_t = inf, and the fallback when the list overflows) must give the same hits, times and totals --
+    and both the C oracle's."""
+    from oracle import coracle
+    cfg = synth.random_target_problem(128, 4, 0, n_free=13, n_target_nodes=4)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    sp = coracle.Space(*args)
+    rec = coracle.target_records(sp, cfg['target node set'], cfg['target substate code'], 300, 100, 8000)
+    want = np.nonzero(rec['reached'])[0] + 100
+    assert len(want) > 7
+    pk = _lib.PackedProblem(*args)
+    tgt = _lib.make_target(cfg['target node set'], cfg['target substate code'], pk.kw)
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt) as plan:
+        _, _, base = plan.target_run(100, 8000, 300)                  # one chunk, one pass
+    with _lib.Plan(pk, _lib.MODE_TARGET, target=tgt, **dict(dict(chunk_log2=10), **opts)) as plan:
+        hit_index, hit_t, st = plan.target_run(100, 8000, 300)
+        assert [int(i) for i in hit_index] == [int(i) for i in want]
+        assert [int(t) for t in hit_t] == [int(rec['stop_t'][i - 100]) for i in want]
+        assert st['n_found'] == len(want)
+        assert (st['steps'], st['n_without'], st['n_found']) == (base['steps'], base['n_without'], base['n_found'])
+        few, _, st3 = plan.target_run(100, 8000, 300, 3)
+        assert [int(i) for i in few] == [int(i) for i in want[:3]] and st3['n_found'] == len(want)
+
+
 def test_no_device_plan_cannot_run():
     cfg = synth.random_attract_problem(8, 2, 0, n_free=4)
     pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
