@@ -142,6 +142,8 @@ def cached_group(packed, mode, devices=None, target=None, **plan_opts):
 def release_cached_plans():
     while _GROUPS:
         _GROUPS.popitem()[1].close()
+    while _ENGINES:
+        _ENGINES.popitem()[1].close()
     _lib.release_cached_memory()
 
 
@@ -190,20 +192,43 @@ def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_prob
         return attract_devices(predecessor_node_lists, truth_tables, origin_simulation_problem,
                                simulation_problem_variations, max_t, max_attractor_l, devices=[device],
                                **plan_opts)
-    eng = AttractEngine(predecessor_node_lists, truth_tables, origin_simulation_problem,
-                        simulation_problem_variations, device=device, rank=rank, world=world,
-                        **plan_opts)
+    eng = cached_engine(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                        simulation_problem_variations, device, rank, world, **plan_opts)
     try:
         eng.run(max_t, max_attractor_l)
         attractors = eng.attractors()
-        h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + eng.plan.cubin_bytes() + \
-            8 * eng.plan.kw * len(attractors)
-        d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * len(a.states) for a in attractors) + 128
-        return {'attractors': attractors, 'n_attractors': len(attractors),
-                'n_found': eng.totals['n_found'], 'n_without': eng.totals['n_without'],
-                'steps_total': eng.totals['steps'], 'h2d_bytes': h2d, 'd2h_bytes': d2h}
-    finally:
+    except Exception:
+        # (a failed run leaves the engine in an unknown state: it is not kept)
+        for key in [k for k, v in _ENGINES.items() if v is eng]:
+            del _ENGINES[key]
         eng.close()
+        raise
+    h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + 8 * eng.plan.kw * len(attractors)
+    d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * len(a.states) for a in attractors) + 128
+    return {'attractors': attractors, 'n_attractors': len(attractors),
+            'n_found': eng.totals['n_found'], 'n_without': eng.totals['n_without'],
+            'steps_total': eng.totals['steps'], 'h2d_bytes': h2d, 'd2h_bytes': d2h}
+
+
+_ENGINES = OrderedDict()         # like _GROUPS, for the one-process-per-GPU form
+
+
+def cached_engine(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                  simulation_problem_variations, device, rank, world, **plan_opts):
+    """This rank's engine (plan, exchange buffers) for this network / problem space, kept across calls:
+    the next job on the same input starts with its first kernel launch."""
+    packed = _lib.PackedProblem(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                                simulation_problem_variations)
+    key = (tuple((name, a.tobytes()) for name, a in sorted(packed.arrays.items())), device, rank, world,
+           tuple(sorted(plan_opts.items())))
+    eng = _ENGINES.pop(key, None)
+    if eng is None:
+        eng = AttractEngine(predecessor_node_lists, truth_tables, origin_simulation_problem,
+                            simulation_problem_variations, device=device, rank=rank, world=world, **plan_opts)
+        while len(_ENGINES) >= _GROUPS_MAX:
+            _ENGINES.popitem(last=False)[1].close()
+    _ENGINES[key] = eng
+    return eng
 
 
 def attract_master(mpi_comm, n_simulation_problem_batches_per_process, origin_simulation_problem,

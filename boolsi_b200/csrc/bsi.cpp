@@ -1625,13 +1625,34 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
         for (uint64_t i = 0; i < n; ++i) hits.push_back({hi[i], ht[i]});
         return BSI_OK;
     };
+    // hits of one list in index order (the enumeration order the reference reports in, simulate.py:149-178).
+    // Only the first `cap - written` are handed out: when that is a small part of the list they are
+    // SELECTED (partial sort, linear in the list), otherwise the list is radix-sorted on the index
+    // (11-bit digits over the bits the indices of this run can have) -- a comparison sort of some
+    // 10^5 hits costs more host time than the kernels of a 2^26-state chunk take.
     auto emit_sorted = [&]() {
-        std::sort(hits.begin(), hits.end());
         total_hits += hits.size();
-        for (auto &h : hits) {
-            if (written >= cap) break;
-            hit_index[written] = h.first;
-            hit_t[written] = h.second;
+        const uint64_t want = std::min<uint64_t>(cap - std::min(written, cap), hits.size());
+        if (want == 0) return;
+        if (want < hits.size() / 8) {
+            std::partial_sort(hits.begin(), hits.begin() + want, hits.end());
+        } else if (hits.size() < 4096) {
+            std::sort(hits.begin(), hits.end());
+        } else {
+            int bits = 1;
+            while (bits < 64 && (idx_end >> bits)) ++bits;
+            std::vector<std::pair<uint64_t, uint64_t>> tmp(hits.size());
+            for (int shift = 0; shift < bits; shift += 11) {
+                size_t count[2049] = {0};
+                for (auto &h : hits) ++count[((h.first >> shift) & 2047u) + 1];
+                for (int d = 0; d < 2048; ++d) count[d + 1] += count[d];
+                for (auto &h : hits) tmp[count[(h.first >> shift) & 2047u]++] = h;
+                hits.swap(tmp);
+            }
+        }
+        for (uint64_t i = 0; i < want; ++i) {
+            hit_index[written] = hits[i].first;
+            hit_t[written] = hits[i].second;
             ++written;
         }
     };

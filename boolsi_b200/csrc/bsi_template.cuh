@@ -1506,66 +1506,23 @@ __device__ __forceinline__ void bsi_finish_word(const BsiFound *found_q, u64 n_f
 #else
 #define BSI_EW_DICT_MIN_LAM BSI_EARLY_DICT_MIN_LAM
 #endif
-// The first BSI_GR_FAST groups of a word and the first BSI_TC_FAST entries of the thread's attractor
-// cache live in SHARED memory, one column per thread ([slot][thread]: no bank conflicts); the rest
-// stays in local memory.  The resolution kernels keep some 4 KB of per-lane arrays per thread in local
-// memory -- 150 MB over the resident grid, more than L1 and L2 hold -- so every access to the
-// group counters and the cache used to be an L1 miss (ncu, cambium2: 60 % of the stall samples of
-// bsi_resolve_early were long-scoreboard waits on exactly these arrays; 3 GB of local-memory
-// write-backs reached DRAM per 2^26 states).  A word rarely has more than four groups, and the
-// cache is kept in the order of its counts, so the shared tier takes nearly all accesses.
-#if BSI_TUNE & 16
-#define BSI_GR_FAST 0
-#define BSI_TC_FAST 0
-#else
-#define BSI_GR_FAST (BSI_KW <= 2 ? 4 : 2)
-#define BSI_TC_FAST (BSI_KW <= 2 ? 4 : 2)
-#endif
-#define BSI_TC64 (BSI_KW + 3)                   // key, n, s1, s2
-#define BSI_GR64 (BSI_KW + 1)                   // key, s2
-#define BSI_GR32 5                              // mask, lam, n | late << 16, s1, jlim
-#define BSI_FAST64 (BSI_TC_FAST * BSI_TC64 + BSI_GR_FAST * BSI_GR64)
-#define BSI_FAST32 (BSI_TC_FAST + BSI_GR_FAST * BSI_GR32)
-// declares the tier in a kernel and binds this thread's columns
-#define BSI_FAST_TIER(F)                                                          \
-    __shared__ u64 fast64_s[(BSI_FAST64 ? BSI_FAST64 : 1) * BSI_BLOCK];           \
-    __shared__ u32 fast32_s[(BSI_FAST32 ? BSI_FAST32 : 1) * BSI_BLOCK];           \
-    BsiFast F;                                                                    \
-    F.w64 = fast64_s + threadIdx.x;                                               \
-    F.w32 = fast32_s + threadIdx.x;
-struct BsiFast { u64 *w64; u32 *w32; };
-
 struct BsiGroups {
     u32 n_groups;
-    BsiFast f;
-    // groups BSI_GR_FAST and up
     u32 mask[32];               // lanes of the group
     u32 lam[32];                // their cycle length
     u64 key[32][BSI_KW];        // their canonical key
-    u32 jlim[32];               // a lane of the group that reaches its cycle at relative time j closes by
+    u64 jlim[32];               // a lane of the group that reaches its cycle at relative time j closes by
                                 // max_t iff j < jlim (mu + lambda <= T, reference model.py:201)
-    u32 nl[32];                 // lanes that close in time (low half) / only after max_t (high half)
+    u32 n[32], late[32];        // lanes that close in time / only after max_t
     u32 s1[32];                 // sum of j over the former (j < 2^24, at most 32 lanes)
     u64 s2[32];                 // sum of j^2
-    unsigned char gid[32];      // lane -> its group (words of more than BSI_GR_FAST groups)
+    unsigned char gid[32];      // lane -> its group
 };
-#define BSI_GR_W32(gr, g, field) (gr).f.w32[(BSI_TC_FAST + (g) * BSI_GR32 + (field)) * BSI_BLOCK]
-#define BSI_GR_W64(gr, g, slot) (gr).f.w64[(BSI_TC_FAST * BSI_TC64 + (g) * BSI_GR64 + (slot)) * BSI_BLOCK]
-__device__ __forceinline__ u32 &bsi_gr_mask(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W32(gr, g, 0); return gr.mask[g]; }
-__device__ __forceinline__ u32 &bsi_gr_lam(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W32(gr, g, 1); return gr.lam[g]; }
-__device__ __forceinline__ u32 &bsi_gr_nl(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W32(gr, g, 2); return gr.nl[g]; }
-__device__ __forceinline__ u32 &bsi_gr_s1(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W32(gr, g, 3); return gr.s1[g]; }
-__device__ __forceinline__ u32 &bsi_gr_jlim(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W32(gr, g, 4); return gr.jlim[g]; }
-__device__ __forceinline__ u64 &bsi_gr_key(BsiGroups &gr, u32 g, int k) { if (g < BSI_GR_FAST) return BSI_GR_W64(gr, g, k); return gr.key[g][k]; }
-__device__ __forceinline__ u64 &bsi_gr_s2(BsiGroups &gr, u32 g) { if (g < BSI_GR_FAST) return BSI_GR_W64(gr, g, BSI_KW); return gr.s2[g]; }
-
 __device__ __forceinline__ void bsi_group_open(BsiGroups &gr, u32 g, u32 mask, u32 lam, u64 T) {
-    bsi_gr_mask(gr, g) = mask;
-    bsi_gr_lam(gr, g) = lam;
-    const u64 jl = (u64)lam <= T ? T - lam + 1ull : 0ull;
-    bsi_gr_jlim(gr, g) = jl > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)jl;     // (j itself stays below 2^24)
-    bsi_gr_nl(gr, g) = 0u; bsi_gr_s1(gr, g) = 0u; bsi_gr_s2(gr, g) = 0ull;
-    // (the lane -> group table is only read in words of more than BSI_GR_FAST groups)
+    gr.mask[g] = mask;
+    gr.lam[g] = lam;
+    gr.jlim[g] = (u64)lam <= T ? T - lam + 1ull : 0ull;
+    gr.n[g] = 0u; gr.late[g] = 0u; gr.s1[g] = 0u; gr.s2[g] = 0ull;
     while (mask) {
         const u32 l = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -1577,33 +1534,32 @@ __device__ __forceinline__ void bsi_group_open(BsiGroups &gr, u32 g, u32 mask, u
 // ordered regime: a few events of many lanes each) are counted per GROUP, one popc each; lanes that
 // close one by one (up to 32 events per word, several groups) per LANE through its group number.
 __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
-    const u32 G = gr.n_groups;
-    if (G > BSI_GR_FAST && (u32)__popc(m) < G) {
+    if ((u32)__popc(m) < gr.n_groups) {
         while (m) {
             const u32 l = __ffs(m) - 1;
             m &= m - 1;
             const u32 g = gr.gid[l];
-            if (j < bsi_gr_jlim(gr, g)) {
-                bsi_gr_nl(gr, g) += 1u;
-                bsi_gr_s1(gr, g) += j;
-                bsi_gr_s2(gr, g) += (u64)j * j;
+            if ((u64)j < gr.jlim[g]) {
+                gr.n[g] += 1u;
+                gr.s1[g] += j;
+                gr.s2[g] += (u64)j * j;
             } else {
-                bsi_gr_nl(gr, g) += 0x10000u;
+                gr.late[g] += 1u;
             }
         }
         return;
     }
 #pragma unroll 1
-    for (u32 g = 0; g < G; ++g) {
-        const u32 cnt = __popc(m & bsi_gr_mask(gr, g));
+    for (u32 g = 0; g < gr.n_groups; ++g) {
+        const u32 cnt = __popc(m & gr.mask[g]);
         if (!cnt) continue;
-        if (j < bsi_gr_jlim(gr, g)) {
+        if ((u64)j < gr.jlim[g]) {
             const u32 cj = cnt * j;
-            bsi_gr_nl(gr, g) += cnt;
-            bsi_gr_s1(gr, g) += cj;
-            bsi_gr_s2(gr, g) += (u64)cj * j;
+            gr.n[g] += cnt;
+            gr.s1[g] += cj;
+            gr.s2[g] += (u64)cj * j;
         } else {
-            bsi_gr_nl(gr, g) += cnt << 16;
+            gr.late[g] += cnt;
         }
     }
 }
@@ -1626,44 +1582,31 @@ __device__ __noinline__ void bsi_early_account(BsiGroups &gr, u32 m, u32 j) {
 #define BSI_TC_WAYS 16
 #endif
 struct BsiTCache {
-    BsiFast f;                  // entries 0 .. BSI_TC_FAST - 1: shared memory (see BSI_FAST_TIER)
     u64 key[BSI_TC_WAYS][BSI_KW];
     u64 n[BSI_TC_WAYS], s1[BSI_TC_WAYS], s2[BSI_TC_WAYS];
     u32 lam[BSI_TC_WAYS];
     u32 used;
 };
-#define BSI_TC_W64(tc, i, slot) (tc).f.w64[((i) * BSI_TC64 + (slot)) * BSI_BLOCK]
-__device__ __forceinline__ u64 &bsi_tc_key(BsiTCache &tc, u32 i, int k) { if (i < BSI_TC_FAST) return BSI_TC_W64(tc, i, k); return tc.key[i][k]; }
-__device__ __forceinline__ u64 &bsi_tc_n(BsiTCache &tc, u32 i) { if (i < BSI_TC_FAST) return BSI_TC_W64(tc, i, BSI_KW); return tc.n[i]; }
-__device__ __forceinline__ u64 &bsi_tc_s1(BsiTCache &tc, u32 i) { if (i < BSI_TC_FAST) return BSI_TC_W64(tc, i, BSI_KW + 1); return tc.s1[i]; }
-__device__ __forceinline__ u64 &bsi_tc_s2(BsiTCache &tc, u32 i) { if (i < BSI_TC_FAST) return BSI_TC_W64(tc, i, BSI_KW + 2); return tc.s2[i]; }
-__device__ __forceinline__ u32 &bsi_tc_lam(BsiTCache &tc, u32 i) { if (i < BSI_TC_FAST) return tc.f.w32[i * BSI_BLOCK]; return tc.lam[i]; }
-__device__ __forceinline__ void bsi_tcache_init(BsiTCache &tc, const BsiFast &f) { tc.used = 0u; tc.f = f; }
-__device__ __forceinline__ void bsi_tcache_write(BsiTCache &tc, u32 i, BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
-    u64 k_[BSI_KW];
-#pragma unroll
-    for (int k = 0; k < BSI_KW; ++k) k_[k] = bsi_tc_key(tc, i, k);
-    bsi_table_add(table, log2_slots, k_, bsi_tc_n(tc, i), bsi_tc_s1(tc, i), bsi_tc_s2(tc, i), bsi_tc_lam(tc, i), ctr);
-}
+__device__ __forceinline__ void bsi_tcache_init(BsiTCache &tc) { tc.used = 0u; }
 __device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n, u64 s1, u64 s2, u32 lam,
                                             BsiSlot *table, u32 log2_slots, BsiCounters *ctr) {
 #pragma unroll 1
     for (u32 i = 0; i < tc.used; ++i) {
         bool same = true;
 #pragma unroll
-        for (int k = 0; k < BSI_KW; ++k) same = same && bsi_tc_key(tc, i, k) == key[k];
+        for (int k = 0; k < BSI_KW; ++k) same = same && tc.key[i][k] == key[k];
         if (same) {
-            const u64 nn = bsi_tc_n(tc, i) + n;
-            bsi_tc_n(tc, i) = nn; bsi_tc_s1(tc, i) += s1; bsi_tc_s2(tc, i) += s2;
+            const u64 nn = tc.n[i] + n;
+            tc.n[i] = nn; tc.s1[i] += s1; tc.s2[i] += s2;
             // (kept in the order of their counts: the attractors that take most of the lanes are found
             //  by the first compare or two; entries swap only when their counts cross)
-            if (i && nn > bsi_tc_n(tc, i - 1u)) {
+            if (i && nn > tc.n[i - 1u]) {
 #pragma unroll
-                for (int k = 0; k < BSI_KW; ++k) { const u64 t = bsi_tc_key(tc, i, k); bsi_tc_key(tc, i, k) = bsi_tc_key(tc, i - 1u, k); bsi_tc_key(tc, i - 1u, k) = t; }
-                u64 t = bsi_tc_n(tc, i); bsi_tc_n(tc, i) = bsi_tc_n(tc, i - 1u); bsi_tc_n(tc, i - 1u) = t;
-                t = bsi_tc_s1(tc, i); bsi_tc_s1(tc, i) = bsi_tc_s1(tc, i - 1u); bsi_tc_s1(tc, i - 1u) = t;
-                t = bsi_tc_s2(tc, i); bsi_tc_s2(tc, i) = bsi_tc_s2(tc, i - 1u); bsi_tc_s2(tc, i - 1u) = t;
-                const u32 tl = bsi_tc_lam(tc, i); bsi_tc_lam(tc, i) = bsi_tc_lam(tc, i - 1u); bsi_tc_lam(tc, i - 1u) = tl;
+                for (int k = 0; k < BSI_KW; ++k) { const u64 t = tc.key[i][k]; tc.key[i][k] = tc.key[i - 1u][k]; tc.key[i - 1u][k] = t; }
+                u64 t = tc.n[i]; tc.n[i] = tc.n[i - 1u]; tc.n[i - 1u] = t;
+                t = tc.s1[i]; tc.s1[i] = tc.s1[i - 1u]; tc.s1[i - 1u] = t;
+                t = tc.s2[i]; tc.s2[i] = tc.s2[i - 1u]; tc.s2[i - 1u] = t;
+                const u32 tl = tc.lam[i]; tc.lam[i] = tc.lam[i - 1u]; tc.lam[i - 1u] = tl;
             }
             return;
         }
@@ -1675,16 +1618,16 @@ __device__ __noinline__ void bsi_tcache_add(BsiTCache &tc, const u64 *key, u64 n
         i = 0u;
 #pragma unroll 1
         for (u32 q = 1; q < BSI_TC_WAYS; ++q)
-            if (bsi_tc_n(tc, q) < bsi_tc_n(tc, i)) i = q;
-        if (n <= bsi_tc_n(tc, i)) {                      // (the newcomer is the smallest: it goes itself)
+            if (tc.n[q] < tc.n[i]) i = q;
+        if (n <= tc.n[i]) {                              // (the newcomer is the smallest: it goes itself)
             bsi_table_add(table, log2_slots, key, n, s1, s2, lam, ctr);
             return;
         }
-        bsi_tcache_write(tc, i, table, log2_slots, ctr);
+        bsi_table_add(table, log2_slots, tc.key[i], tc.n[i], tc.s1[i], tc.s2[i], tc.lam[i], ctr);
     }
 #pragma unroll
-    for (int k = 0; k < BSI_KW; ++k) bsi_tc_key(tc, i, k) = key[k];
-    bsi_tc_n(tc, i) = n; bsi_tc_s1(tc, i) = s1; bsi_tc_s2(tc, i) = s2; bsi_tc_lam(tc, i) = lam;
+    for (int k = 0; k < BSI_KW; ++k) tc.key[i][k] = key[k];
+    tc.n[i] = n; tc.s1[i] = s1; tc.s2[i] = s2; tc.lam[i] = lam;
 }
 // the end of the kernel: with WARP_AGG a warp collective (every thread of the warp calls), entry by
 // entry, so that the threads of a warp that hold the same key write it once
@@ -1697,11 +1640,11 @@ __device__ __forceinline__ void bsi_tcache_flush(BsiTCache &tc, BsiSlot *table, 
             if (!__any_sync(0xFFFFFFFFu, mine)) break;
             u64 key0[BSI_KW];
 #pragma unroll
-            for (int k = 0; k < BSI_KW; ++k) key0[k] = mine ? bsi_tc_key(tc, i, k) : 0ull;
-            bsi_warp_table_add(table, log2_slots, key0, mine ? bsi_tc_n(tc, i) : 0ull, mine ? bsi_tc_s1(tc, i) : 0ull,
-                               mine ? bsi_tc_s2(tc, i) : 0ull, mine ? bsi_tc_lam(tc, i) : 0u, ctr);
+            for (int k = 0; k < BSI_KW; ++k) key0[k] = mine ? tc.key[i][k] : 0ull;
+            bsi_warp_table_add(table, log2_slots, key0, mine ? tc.n[i] : 0ull, mine ? tc.s1[i] : 0ull,
+                               mine ? tc.s2[i] : 0ull, mine ? tc.lam[i] : 0u, ctr);
         } else if (mine) {
-            bsi_tcache_write(tc, i, table, log2_slots, ctr);
+            bsi_table_add(table, log2_slots, tc.key[i], tc.n[i], tc.s1[i], tc.s2[i], tc.lam[i], ctr);
         }
     }
     tc.used = 0u;
@@ -1757,7 +1700,7 @@ __device__ __noinline__ bool bsi_early_dict(const BsiDict &dict, const u32 *y, u
         todo &= ~g;
         bsi_group_open(gr, G, g, lam_[l0], T);
 #pragma unroll
-        for (int i = 0; i < BSI_KW; ++i) bsi_gr_key(gr, G, i) = cyc ? keys_[l0][i] : cw_[l0][i];
+        for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = cyc ? keys_[l0][i] : cw_[l0][i];
         ++G;
     }
     gr.n_groups = G;
@@ -1772,7 +1715,6 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
                                                u64 &n_acc, u64 &n_rej) {
     BsiGroups gr;
     gr.n_groups = 0u;
-    gr.f = tc.f;
     {
         BSI_FOR_NODES(BSI_DECL_A)
         BSI_FOR_NODES(BSI_DECL_B)
@@ -1874,7 +1816,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
                     if ((evm[k] >> l0) & 1u) { lam0 = evl[k]; break; }
                 bsi_group_open(gr, G, g, lam0, T);
 #pragma unroll
-                for (int i = 0; i < BSI_KW; ++i) bsi_gr_key(gr, G, i) = (u64)kc_[2 * i] | ((u64)kc_[2 * i + 1] << 32);
+                for (int i = 0; i < BSI_KW; ++i) gr.key[G][i] = (u64)kc_[2 * i] | ((u64)kc_[2 * i + 1] << 32);
                 ++G;
             }
             gr.n_groups = G;
@@ -1883,13 +1825,9 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
 #pragma unroll 1
                 for (u32 g = 0; g < G; ++g) {
                     u32 base, slot;
-                    const u32 lam_g = bsi_gr_lam(gr, g);
-                    u64 k_[BSI_KW];
-#pragma unroll
-                    for (int i = 0; i < BSI_KW; ++i) k_[i] = bsi_gr_key(gr, g, i);
                     // (short cycles too: a word that holds a long one asks the dictionary for all of them)
-                    if (lam_g > 1u && bsi_dict_claim(dict, k_, lam_g, base, slot))
-                        bsi_dict_learn(dict, k_, lam_g, base, slot);
+                    if (gr.lam[g] > 1u && bsi_dict_claim(dict, gr.key[g], gr.lam[g], base, slot))
+                        bsi_dict_learn(dict, gr.key[g], gr.lam[g], base, slot);
                 }
             }
         }
@@ -1948,8 +1886,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
     // ---- the groups' totals: acceptance (reference attract.py:287-300) and aggregation ----------
 #pragma unroll 1
     for (u32 g = 0; g < gr.n_groups; ++g) {
-        const u32 nl = bsi_gr_nl(gr, g);
-        const u64 n = nl & 0xFFFFu, late = nl >> 16, lam = bsi_gr_lam(gr, g), s1 = bsi_gr_s1(gr, g);
+        const u64 n = gr.n[g], late = gr.late[g], lam = gr.lam[g], s1 = gr.s1[g];
         steps += n * (BSI_LP_ORIGIN + lam) + s1          // the loop stops at t = mu + lambda (model.py:201)
                  + late * stop_t_cap;                    // or runs out at max_t
         n_rej += late;
@@ -1959,10 +1896,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
             n_acc += n;
             // trajectory_l = lp + j (attract.py:298): sums of (lp + j) and (lp + j)^2 from those of j
             const u64 lp = BSI_LP_ORIGIN;
-            u64 k_[BSI_KW];
-#pragma unroll
-            for (int i = 0; i < BSI_KW; ++i) k_[i] = bsi_gr_key(gr, g, i);
-            bsi_tcache_add(tc, k_, n, s1 + n * lp, bsi_gr_s2(gr, g) + 2ull * lp * s1 + n * lp * lp, (u32)lam,
+            bsi_tcache_add(tc, gr.key[g], n, s1 + n * lp, gr.s2[g] + 2ull * lp * s1 + n * lp * lp, (u32)lam,
                            table, log2_slots, ctr);
         }
     }
@@ -2014,9 +1948,8 @@ bsi_resolve_early(void *early_base, u64 early_cap, const u64 *n_early_p, const u
     if (bsi_latency_mode(*n_found_p, ctr, few_words)) return;    // bsi_resolve takes the early words too
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
-    BSI_FAST_TIER(fast)
     BsiTCache tc;
-    bsi_tcache_init(tc, fast);
+    bsi_tcache_init(tc);
     for (;;) {
         const u64 e = bsi_grab_word(&ctr->next_word4);
         if (__all_sync(0xFFFFFFFFu, e >= n_early)) break;
@@ -2085,9 +2018,8 @@ bsi_resolve(BsiFound *found_q, const u64 *n_found_p, u64 few_words, void *early_
     const u64 e32 = (n_early + 31) & ~31ull;
     const BsiEarlyQ eq = bsi_early_view(early_base, early_cap);
     u64 steps = 0, n_acc = 0, n_rej = 0;
-    BSI_FAST_TIER(fast)
     BsiTCache tc;
-    bsi_tcache_init(tc, fast);
+    bsi_tcache_init(tc);
     for (;;) {
         const u64 t = bsi_grab_word(&ctr->next_word2);
         if (__all_sync(0xFFFFFFFFu, t >= 2 * w32 + e32)) break;
