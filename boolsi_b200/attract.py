@@ -46,16 +46,33 @@ class AttractEngine:
                  simulation_problem_variations, device=0, rank=0, world=1, **plan_opts):
         self.packed = _lib.PackedProblem(predecessor_node_lists, truth_tables,
                                          origin_simulation_problem, simulation_problem_variations)
-        self.plan = _lib.Plan(self.packed, _lib.MODE_ATTRACT, device=device, **plan_opts)
         self.rank, self.world, self.device = rank, world, device
+        self.plan_opts = dict(plan_opts)
+        self.plan = None
+        self._open_plan()
         self.n_problems = self.packed.n_problems
         self.lo, self.hi = shard_range(self.n_problems, rank, world)
         self._gather = None
         self.totals = None
-        if world > 1:
+
+    def _open_plan(self):
+        if self.plan is not None:
+            self.plan.close()
+        self.plan = _lib.Plan(self.packed, _lib.MODE_ATTRACT, device=self.device, **self.plan_opts)
+        if self.world > 1:
             import torch
             # everything on torch's current stream so that the collective is ordered after the kernels
             self.plan.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def _grow_table(self):
+        """More attractors than the device table holds: the reference's store simply grows
+        (attract.py:405-455), so the table is made eight times larger and the job run again.  Every
+        rank takes this decision from the same gathered headers, so all of them grow together."""
+        log2 = self.plan_opts.get('table_log2_slots') or 20
+        if log2 >= 28:
+            raise _lib.BsiError(-4, 'attractor table overflow at 2^28 slots')
+        self.plan_opts['table_log2_slots'] = min(28, log2 + 3)
+        self._open_plan()
 
     def close(self):
         self.plan.close()
@@ -64,24 +81,39 @@ class AttractEngine:
         """Clear the table, run this rank's problems, merge all ranks' tables (world > 1).
         Afterwards every rank holds the complete table on its device.
         :return: run stats of this rank (`steps` etc.) + job totals in `self.totals`"""
-        self.plan.table_clear()
-        if self.world == 1:
-            st = self.plan.attract_run(self.lo, self.hi, max_t, max_attractor_l)
-            self.totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
+        while True:
+            self.plan.table_clear()
+            if self.world == 1:
+                try:
+                    st = self.plan.attract_run(self.lo, self.hi, max_t, max_attractor_l)
+                except _lib.BsiError as e:
+                    if e.status != -4:
+                        raise
+                    self._grow_table()
+                    continue
+                self.totals = {'steps': st['steps'], 'n_found': st['n_found'], 'n_without': st['n_without']}
+                return st
+            # kernels, table export and the collective are enqueued back to back; the first host
+            # synchronisation is the read of the gathered headers.  A rank whose run fails still takes
+            # part in the collective (its header carries an error mark), so that the others do not wait
+            # for it forever; every rank then raises.
+            failure = None
+            try:
+                self.plan.attract_run_async(self.lo, self.hi, max_t, max_attractor_l)
+            except _lib.BsiError as e:
+                failure = e
+            totals = self._merge_over_ranks(failure)
+            if totals is None:                  # some rank's table overflowed: all ranks grow and repeat
+                try:
+                    self.plan.attract_run_finish()
+                except _lib.BsiError:
+                    pass
+                self._grow_table()
+                continue
+            self.totals = totals
+            st = self.plan.attract_run_finish()
+            st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
             return st
-        # kernels, table export and the collective are enqueued back to back; the first host
-        # synchronisation is the read of the gathered headers.  A rank whose run fails still takes
-        # part in the collective (its header carries an error mark), so that the others do not wait
-        # for it forever; every rank then raises.
-        failure = None
-        try:
-            self.plan.attract_run_async(self.lo, self.hi, max_t, max_attractor_l)
-        except _lib.BsiError as e:
-            failure = e
-        self.totals = self._merge_over_ranks(failure)
-        st = self.plan.attract_run_finish()
-        st['launches'] += 1 + (self.rank > 0) + (self.rank < self.world - 1)    # export + merges
-        return st
 
     def _merge_over_ranks(self, failure=None):
         from .sharding import exchange_tables
@@ -101,7 +133,7 @@ class AttractEngine:
             bad = [r for r in range(self.world) if int(headers[r, 5]) >= 2]
             raise _lib.BsiError(-2, 'the run failed on rank(s) %s' % bad)
         if int(headers[:, 5].max()):
-            raise _lib.BsiError(-4, 'attractor table overflow on some rank (raise table_log2_slots)')
+            return None                 # attractor table overflow on some rank: see run()
         # fold the OTHER ranks' records into this rank's table (header rows and unused rows have
         # n == 0 and are skipped by the merge kernel): two launches, no host synchronisation
         rows = everyone.shape[1]

@@ -338,6 +338,22 @@ def test_attractor_table_overflow_is_reported():
         assert plan.table_count() == 1 << n and st['n_found'] == 1 << n and st['steps'] == 1 << n
 
 
+def test_engine_grows_its_table_instead_of_failing():
+    """The per-rank engine (what attract_sharded and bench.py run) repeats the job with a larger table when
+    the attractors do not fit, as the reference's store simply grows (attract.py:405-455)."""
+    from boolsi_b200.attract import AttractEngine
+    n = 14
+    preds = [[i] for i in range(n)]
+    tts = [{(False,): False, (True,): True} for _ in range(n)]
+    eng = AttractEngine(preds, tts, ([False] * n, {}, {}), (list(range(n)), [], []), table_log2_slots=10)
+    try:
+        st = eng.run(inf, inf)
+        assert eng.plan_opts['table_log2_slots'] >= 16
+        assert eng.plan.table_count() == 1 << n and st['n_found'] == 1 << n and st['steps'] == 1 << n
+    finally:
+        eng.close()
+
+
 def test_attract_long_cap_goes_through_several_rounds():
     """max_t beyond the first horizon in the chaotic regime: rounds 1024 -> cap (most lanes stay
     open), results equal to the oracle's."""
