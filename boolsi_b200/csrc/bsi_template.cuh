@@ -1275,26 +1275,47 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
                 }
             }
             BSI_PACK(b, cw_)
-            // ---- b <- P(c0): advance each lane by its own number of steps ---------------------
-#define BSI_HOLD_NODE(i) b##i = bsi_lop3<0xCA>(go_, c##i, b##i);
-            {
-                u32 go_ = 0u, next_ev = 0u;
-                for (u32 k = 0; k < adv_max; ++k) {
-                    if (k == next_ev) {
-                        go_ = 0u;
-                        next_ev = 0xFFFFFFFFu;
-#pragma unroll 1
-                        for (u32 l = 0; l < 32; ++l) {
-                            if (!((valid >> l) & 1u)) continue;
-                            u32 adv = aux_s[l * BSI_BLOCK + tid];
-                            if (adv > k) { go_ |= 1u << l; next_ev = min(next_ev, adv); }
-                        }
-                    }
+            // ---- b <- P(c0): y advanced by each lane's own number of steps.  ONE plain walk of adv_max
+            //      steps (b -> c -> b, no per-step hold of the lanes that are done); the lanes whose advance
+            //      is k are latched into a -- free until x_c0 is built below -- when the walk is k steps
+            //      old: an event costs one pass over the nodes, and a word has at most 32 of them ----------
+#define BSI_LATCH_A(i) a##i = bsi_lop3<0xCA>(m_, X_(i), a##i);
+#define BSI_ADV_EVENT(K)                                                          \
+    {                                                                             \
+        u32 m_ = 0u, nx_ = 0xFFFFFFFFu;                                           \
+        _Pragma("unroll 1")                                                       \
+        for (u32 l = 0; l < 32; ++l) {                                            \
+            if (!((valid >> l) & 1u)) continue;                                   \
+            const u32 adv = aux_s[l * BSI_BLOCK + tid];                           \
+            if (adv == (K)) m_ |= 1u << l;                                        \
+            else if (adv > (K)) nx_ = min(nx_, adv);                              \
+        }                                                                         \
+        next_ev = nx_;                                                            \
+        BSI_FOR_NODES(BSI_LATCH_A)                                                \
+    }
+            if (adv_max) {
+                u32 next_ev = 0u;
+#define X_(i) b##i
+                BSI_FOR_NODES(BSI_ZERO_A)
+                BSI_ADV_EVENT(0u)                        // (advance 0: P(c0) = y)
+#undef X_
+                for (u32 k = 1; k <= adv_max; k += 2) {
                     BSI_UPDATE(c, b)
-                    BSI_FOR_NODES(BSI_HOLD_NODE)
+#define X_(i) c##i
+                    if (k == next_ev) BSI_ADV_EVENT(k)
+#undef X_
+                    if (k + 1u > adv_max) break;
+                    BSI_UPDATE(b, c)
+#define X_(i) b##i
+                    if (k + 1u == next_ev) BSI_ADV_EVENT(k + 1u)
+#undef X_
                 }
+#define BSI_COPY_BA(i) b##i = a##i;
+                BSI_FOR_NODES(BSI_COPY_BA)
+#undef BSI_COPY_BA
             }
-#undef BSI_HOLD_NODE
+#undef BSI_ADV_EVENT
+#undef BSI_LATCH_A
         }
         // ---- a <- x_c0: from the problem index (c0 = 0) or the shipped checkpoint state -----------
         {

@@ -24,7 +24,12 @@ a = goldenlib.case_args(case)
 t_in = time.perf_counter()
 if %(impl)r == 'b200':
     import boolsi_b200
-    from boolsi_b200 import db
+    from boolsi_b200 import db, _lib
+    t_a = time.perf_counter()
+    n_dev = _lib.device_count()                 # (first driver call of the process: cuInit)
+    t_b = time.perf_counter()
+    print('LAP import_boolsi_b200 %%.4f' %% (t_a - t_in))
+    print('LAP cuInit_and_device_count %%.4f (%%d devices)' %% (t_b - t_a, n_dev))
     conn = db.ResultStore() if hasattr(db, 'ResultStore') else db.new_db_conn()
     if case['mode'] == 'attract':
         n = boolsi_b200.attract_master(None, 1, a['origin'], a['variations'], a['preds'], a['tts'], a['max_t'],
@@ -59,7 +64,12 @@ def child(case, impl, env):
     for line in out.stdout.splitlines():
         if line.startswith('RESULT'):
             _, n, total, job = line.split()
-            return {'results': int(n), 'process_s': float(total), 'job_s': float(job)}
+            r = {'results': int(n), 'process_s': float(total), 'job_s': float(job)}
+            r['python_laps'] = [ln[4:] for ln in out.stdout.splitlines() if ln.startswith('LAP ')]
+            laps = [ln[6:].split() for ln in out.stderr.splitlines() if ln.startswith('[bsi] ')]
+            if laps:        # BSI_DEBUG_TIMING=1: the library's own stages, ms
+                r['stages_ms'] = [[' '.join(x[:-2]), float(x[-2])] for x in laps if len(x) >= 3]
+            return r
     raise RuntimeError('child failed:\n' + out.stdout[-2000:] + out.stderr[-4000:])
 
 
@@ -68,8 +78,8 @@ def main():
     line = {}
     for case in cases:
         with tempfile.TemporaryDirectory() as cache:
-            cold = child(case, 'b200', dict(os.environ, BSI_CACHE_DIR=cache))
-            warm = child(case, 'b200', dict(os.environ, BSI_CACHE_DIR=cache))
+            cold = child(case, 'b200', dict(os.environ, BSI_CACHE_DIR=cache, BSI_DEBUG_TIMING='1'))
+            warm = child(case, 'b200', dict(os.environ, BSI_CACHE_DIR=cache, BSI_DEBUG_TIMING='1'))
         line[case] = {'b200_cold': cold, 'b200_warm_disk_cache': warm}
         try:
             line[case]['reference_cpu'] = child(case, 'reference', dict(os.environ))
