@@ -152,6 +152,11 @@ class AttractEngine:
 
 _GROUPS = OrderedDict()          # (descriptor bytes, mode, devices, options) -> _lib.Group, most recent last
 _GROUPS_MAX = 2
+#: A job of at most this many problems runs on ONE device when the caller names none: a B200 holds
+#: 37 888 words of 32 problems in flight, so fewer words than that finish in one wave on one GPU and
+#: more GPUs cannot shorten it -- while every further device costs its CUDA context (0.35 s warm, over
+#: a second on a cold box: profiles/README.md, small-job latency).
+SMALL_JOB_PROBLEMS = 1 << 20
 
 
 def cached_group(packed, mode, devices=None, target=None, **plan_opts):
@@ -159,6 +164,8 @@ def cached_group(packed, mode, devices=None, target=None, **plan_opts):
     job on the same input skips kernel specialisation, module loading and buffer allocation -- the
     per-run set-up the reference repeats per batch (mpi.py:351-376, 525-528).  At most two groups
     stay alive; `release_cached_plans()` drops them."""
+    if devices is None and packed.n_problems <= SMALL_JOB_PROBLEMS:
+        devices = [0]
     key = (tuple((name, a.tobytes()) for name, a in sorted(packed.arrays.items())), mode,
            None if devices is None else tuple(int(d) for d in devices),
            None if target is None else bytes(target), tuple(sorted(plan_opts.items())))

@@ -130,8 +130,12 @@ def test_target_and_simulate_groups_equal_the_plans():
 
 
 def test_masters_use_every_visible_gpu(caplog):
+    """...for jobs that can use them: a job of fewer words than one GPU holds in flight stays on one device
+    (more devices could not shorten it and each costs a CUDA context)."""
     import logging
-    args, pk = _attract_problem(64, 3, 1, 16)
+    from boolsi_b200.attract import SMALL_JOB_PROBLEMS
+    args, pk = _attract_problem(64, 3, 1, 21)
+    assert pk.n_problems > SMALL_JOB_PROBLEMS
 
     class Comm:
         n_workers = 0
@@ -140,6 +144,12 @@ def test_masters_use_every_visible_gpu(caplog):
         n = boolsi_b200.attract_master(Comm(), 100, args[2], args[3], args[0], args[1], 1000, inf, pk.n_problems,
                                        True, db, False, None)
     assert any('Used %d GPU(s)' % _n_gpus() in r.getMessage() for r in caplog.records)
+    small_args, small_pk = _attract_problem(64, 3, 1, 12)
+    caplog.clear()
+    with caplog.at_level(logging.INFO):
+        boolsi_b200.attract_master(Comm(), 100, small_args[2], small_args[3], small_args[0], small_args[1], 1000, inf,
+                                   small_pk.n_problems, True, boolsi_b200.ResultStore(), False, None)
+    assert any('Used 1 GPU(s)' in r.getMessage() for r in caplog.records)
     db1 = boolsi_b200.ResultStore()
     n1 = boolsi_b200.attract_master(Comm(), 100, args[2], args[3], args[0], args[1], 1000, inf, pk.n_problems,
                                     True, db1, False, None, devices=[0])
