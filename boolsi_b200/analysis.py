@@ -26,7 +26,8 @@ def node_activity(attractors):
     frequencies = np.array([a.frequency for a in attractors], dtype=np.int64)
     counts = [getattr(a, 'node_on_counts', None) for a in attractors]
     if attractors and all(c is not None for c in counts):
-        lengths = np.array([len(a.states) for a in attractors], dtype=np.float64)
+        lengths = np.array([a.n_states if hasattr(a, 'n_states') else len(a.states) for a in attractors],
+                           dtype=np.float64)
         observations = np.asarray(counts, dtype=np.float64) / lengths[:, None]
     else:
         observations = np.array([np.asarray(a.states, dtype=np.float64).mean(axis=0) for a in attractors])

@@ -25,11 +25,21 @@ from .problems import shard_range
 class AggregatedAttractor:
     """Result record with the attributes the reference's consumers read (attract.py:18-45):
     `states` (min-code state first, cycle order), `frequency`, `trajectory_l_mean`,
-    `trajectory_l_variation_sum` -- the last two derived from the exact integer triple."""
+    `trajectory_l_variation_sum` -- the last two derived from the exact integer triple.
+
+    `states` may be given as the reference's list of lists of bool or PACKED -- `(uint64 words
+    [n_states, key_words], n_nodes)`, what the device returns.  Packed states stay packed (8 bytes per
+    64 nodes and state) until a consumer asks: `states_array` (bool array [n_states, n_nodes]) and
+    `states` (list of lists of bool, what the reference's writers read) are made on first use;
+    `n_states` needs neither."""
 
     def __init__(self, key, states, frequency, sum_l, sum_l2, node_on_counts=None):
         self.key = key
-        self.states = states
+        self._words = self._array = self._states = None
+        if isinstance(states, tuple):
+            self._words, self._n_nodes = states
+        else:
+            self._states = states
         self.frequency = frequency
         # in how many states of the cycle each node is on, counted on the device (the input of the
         # node-correlation analysis, attractor_analysis.py:49-51), or None
@@ -37,6 +47,23 @@ class AggregatedAttractor:
         self.sum_l, self.sum_l2 = sum_l, sum_l2
         self.trajectory_l_mean = float(Fraction(sum_l, frequency))
         self.trajectory_l_variation_sum = float(Fraction(sum_l2) - Fraction(sum_l * sum_l, frequency))
+
+    @property
+    def n_states(self):
+        return len(self._words) if self._words is not None else len(self._states)
+
+    @property
+    def states_array(self):
+        if self._array is None:
+            self._array = _lib.state_array_from_word_rows(self._words, self._n_nodes) \
+                if self._words is not None else np.asarray(self._states, dtype=bool)
+        return self._array
+
+    @property
+    def states(self):
+        if self._states is None:
+            self._states = self.states_array.tolist()
+        return self._states
 
 
 class AttractEngine:
@@ -193,7 +220,7 @@ def read_attractors(plan, n_nodes):
             for r in plan.table_read()]
     rows.sort(key=lambda x: (-x[1], x[0]))
     orbits, counts = plan.attractor_orbits([(key, lam) for key, _, _, _, lam in rows], with_activity=True)
-    return [AggregatedAttractor(key, _lib.states_from_word_rows(words, n_nodes), n, s1, s2, on)
+    return [AggregatedAttractor(key, (words, n_nodes), n, s1, s2, on)
             for (key, n, s1, s2, lam), words, on in zip(rows, orbits, counts)]
 
 
@@ -215,7 +242,7 @@ def attract_devices(predecessor_node_lists, truth_tables, origin_simulation_prob
     plan = group.plan(0)
     attractors = read_attractors(plan, packed.n_nodes)
     h2d = sum(a.nbytes for a in packed.arrays.values()) + 8 * plan.kw * len(attractors)
-    d2h = 64 * len(attractors) + sum(8 * plan.kw * len(a.states) for a in attractors) + 128 * group.n_devices
+    d2h = 64 * len(attractors) + sum(8 * plan.kw * a.n_states for a in attractors) + 128 * group.n_devices
     return {'attractors': attractors, 'n_attractors': len(attractors), 'n_found': total['n_found'],
             'n_without': total['n_without'], 'steps_total': total['steps'], 'h2d_bytes': h2d,
             'd2h_bytes': d2h, 'n_devices': group.n_devices, 'stats': total, 'per_device': per_device}
@@ -243,7 +270,7 @@ def attract_sharded(predecessor_node_lists, truth_tables, origin_simulation_prob
         eng.close()
         raise
     h2d = sum(a.nbytes for a in eng.packed.arrays.values()) + 8 * eng.plan.kw * len(attractors)
-    d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * len(a.states) for a in attractors) + 128
+    d2h = 64 * len(attractors) + sum(8 * eng.plan.kw * a.n_states for a in attractors) + 128
     return {'attractors': attractors, 'n_attractors': len(attractors),
             'n_found': eng.totals['n_found'], 'n_without': eng.totals['n_without'],
             'steps_total': eng.totals['steps'], 'h2d_bytes': h2d, 'd2h_bytes': d2h}

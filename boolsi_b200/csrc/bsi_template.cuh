@@ -2436,17 +2436,19 @@ bsi_target_main(u64 idx_begin, const u64 *in_queue, u64 n_lanes, u64 T, int chec
     }
 
     u64 steps = 0;
+    // the word's hits take consecutive places of the list, in lane (= index) order: one atomic per word
+    u64 pos = (hit & valid) ? atomicAdd(&ctr->n_hits, (u64)__popc(hit & valid)) : 0ull;
 #pragma unroll 1
     for (u32 l = 0; l < 32; ++l) {
         if (!((valid >> l) & 1u)) continue;
         u64 q = (w << 5) + l;
         u64 idx = in_queue ? in_queue[q] : idx_begin + q;
         if ((hit >> l) & 1u) {
-            u64 pos = atomicAdd(&ctr->n_hits, 1ull);
             if (pos < hit_cap) {
                 hit_idx[pos] = idx;
                 hit_t[pos] = th_s[l * BSI_BLOCK + threadIdx.x];
             }
+            ++pos;
             steps += th_s[l * BSI_BLOCK + threadIdx.x];
         } else if (check_closure && ((closed >> l) & 1u)) {
             closed_q[atomicAdd(&ctr->n_found, 1ull)] = idx;
