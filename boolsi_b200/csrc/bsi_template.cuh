@@ -862,6 +862,51 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                     }
                 }
             }
+            // Lanes that matched a FINAL checkpoint take y (that checkpoint) and z (the one before it) out
+            // of the bit-sliced checkpoint words.  One or two lanes: bit by bit (64 single-bit moves per
+            // state).  More -- the closing-heavy chaotic regime, a handful of lanes in every word -- : the
+            // checkpoints these lanes need go through 32x32 transposes once, for all 32 lanes together
+            // (ncu, seed-2 network: the bit-by-bit form was 12 % of the kernel's instructions).
+            u32 defer = 0u, need = 0u;
+            {
+                u32 m = F;
+                while (m) {
+                    const u32 l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u32 c0 = c_s[(32 + l) * sstride];
+                    if (c0 & BSI_DEFERRED) {
+                        const u32 slot = c0 & 3u;
+                        defer |= 1u << l;
+                        need |= (1u << slot) | (slot ? 1u << (slot - 1u) : 0u);
+                    }
+                }
+            }
+            // (BSI_TUNE 32: from the first lane on, 64: never -- the tests run both forms on the same inputs)
+            const bool by_transpose = (BSI_TUNE & 64) ? false : (u32)__popc(defer) >= ((BSI_TUNE & 32) ? 1u : 3u);
+            u64 ckw_[3][32][BSI_KW];
+            if (by_transpose) {
+#pragma unroll 1
+                for (u32 s = 0; s < 3u; ++s) {
+                    if (!((need >> s) & 1u)) continue;
+                    const u32 *p = BSI_CK_PTR(s);
+                    const u64 st = BSI_CK_STRIDE(s);
+#pragma unroll 1
+                    for (u32 b = 0; b < (u32)((BSI_N + 31) / 32); ++b) {
+                        unsigned int A_[32];
+#pragma unroll 8
+                        for (u32 k = 0; k < 32; ++k) {
+                            const u32 node = 32u * b + 31u - k;       // (the transpose reverses both indices)
+                            A_[k] = node < (u32)BSI_N ? p[node * st] : 0u;
+                        }
+                        bsi_transpose32_call(A_);
+#pragma unroll 8
+                        for (u32 k = 0; k < 32; ++k) {
+                            if (b & 1u) ckw_[s][31u - k][b >> 1] |= (u64)A_[k] << 32;
+                            else ckw_[s][31u - k][b >> 1] = (u64)A_[k];
+                        }
+                    }
+                }
+            }
             u32 m = F;
             while (m) {
                 u32 l = __ffs(m) - 1;
@@ -880,6 +925,13 @@ __device__ __forceinline__ void bsi_main_body(u64 word0, u64 n_words, u64 idx_be
                     const u32 *pz = BSI_CK_PTR(slot ? slot - 1u : 0u);
                     const u64 sz = BSI_CK_STRIDE(slot ? slot - 1u : 0u);
                     r.c0 = slot == 0u ? 0u : (slot == 1u ? st0 : st1);
+                    if (by_transpose) {
+#pragma unroll
+                        for (int k = 0; k < BSI_KW; ++k) {
+                            const u64 y = ckw_[slot][l][k];
+                            r.y[k] = y; r.key[k] = y; r.z[k] = slot ? ckw_[slot - 1u][l][k] : 0ull;
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < BSI_KW; ++k) {
                         u64 y = 0ull, z = 0ull;

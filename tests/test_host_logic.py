@@ -202,3 +202,48 @@ def test_three_rank_hit_exchange_over_gloo(tmp_path, n_to_find):
     for r in range(world):
         index, t, tot = np.load(os.path.join(str(tmp_path), 'h%d.npy' % r), allow_pickle=True).tolist()
         assert [int(i) for i in index] == want_idx and [int(x) for x in t] == want_t and tot == [total]
+
+
+def test_aggregated_attractor_keeps_packed_states_until_asked():
+    """The device returns state codes; the record converts them to the reference's list of lists of
+    bool (attract.py:18-45 consumers) only when `states` is read, and both forms agree."""
+    from boolsi_b200 import _lib
+    from boolsi_b200.attract import AggregatedAttractor
+    n_nodes = 70
+    codes = [0x3FFFFFFFFFFFFFFFFF, 5, (1 << 69) | 1]
+    words = np.array([_lib.words_from_code(c, 2) for c in codes], np.uint64)
+    packed = AggregatedAttractor(5, (words, n_nodes), 4, 10, 30)
+    assert packed._states is None and packed.n_states == 3
+    want = [[bool((c >> i) & 1) for i in range(n_nodes)] for c in codes]
+    assert packed.states == want and packed.states is packed.states
+    assert packed.states_array.shape == (3, n_nodes) and packed.states_array.tolist() == want
+    plain = AggregatedAttractor(5, want, 4, 10, 30)
+    assert plain.n_states == 3 and plain.states is want and plain.states_array.tolist() == want
+    assert (packed.trajectory_l_mean, packed.trajectory_l_variation_sum) == (2.5, 5.0)
+
+
+def test_small_jobs_stay_on_one_device(monkeypatch):
+    """cached_group: no device list + a job of at most SMALL_JOB_PROBLEMS problems -> device 0 only (more
+    devices cannot shorten a job of less than one wave and each costs a CUDA context); larger jobs and
+    explicit lists are passed through."""
+    from boolsi_b200 import _lib, attract
+    seen = []
+
+    class FakeGroup:
+        def __init__(self, packed, mode, devices=None, target=None, **opts):
+            seen.append(devices)
+
+        def close(self):
+            pass
+    monkeypatch.setattr(_lib, 'Group', FakeGroup)
+    attract.release_cached_plans()
+    try:
+        small = synth.random_attract_problem(64, 3, 0, n_free=10)
+        big = synth.random_attract_problem(64, 3, 0, n_free=21)
+        for cfg, devices in ((small, None), (big, None), (small, [0, 1])):
+            pk = _lib.PackedProblem(cfg['incoming node lists'], cfg['truth tables'],
+                                    cfg['origin simulation problem'], cfg['simulation problem variations'])
+            attract.cached_group(pk, _lib.MODE_ATTRACT, devices)
+        assert seen == [[0], None, [0, 1]]
+    finally:
+        attract._GROUPS.clear()

@@ -126,6 +126,24 @@ def test_emulated_kernels_with_checkpoints_in_scratch(opts, tmp_path):
     _check(exe, space, 3, 300, 120, inf, first_horizon=16, few_words=1)
 
 
+@pytest.mark.parametrize('tune', [32, 64], ids=['by-transpose', 'bit-by-bit'])
+@pytest.mark.parametrize('n_nodes,k,seed', [(64, 3, 2), (72, 3, 2), (72, 3, 0)])
+def test_emulated_extraction_of_final_checkpoint_states(n_nodes, k, seed, tune, tmp_path):
+    """Lanes that match a FINAL checkpoint ship y (that checkpoint) and z (the one before it): both
+    extraction forms -- 32x32 transposes of the checkpoints for all lanes of the word, single-bit moves
+    per lane -- forced on the same inputs: chaotic networks whose closing lanes match the final checkpoints
+    (4 to 32 such lanes per word; 72 nodes = two key words and a partial third 32-node block)."""
+    cfg = synth.random_attract_problem(n_nodes, k, seed, n_free=9)
+    args = (cfg['incoming node lists'], cfg['truth tables'], cfg['origin simulation problem'],
+            cfg['simulation problem variations'])
+    space = coracle.Space(*args)
+    pk = _lib.PackedProblem(*args)
+    exe = _build(tmp_path, pk, tune=tune)
+    for first_horizon, few_words in ((1, 0), (3, 1), (16, 1), (0, 0)):
+        _check(exe, space, 0, pk.n_problems, 1000, inf, first_horizon=first_horizon, few_words=few_words, no_early=1)
+    _check(exe, space, 5, 300, 90, 40, first_horizon=4)
+
+
 @pytest.mark.parametrize('n_nodes,k,seed,max_t', [(160, 2, 3, 300), (256, 2, 1, 400)])
 def test_emulated_kernels_at_the_maximum_network_size(n_nodes, k, seed, max_t, tmp_path):
     """Three and four key words per state: beyond the golden fixtures (128 nodes)."""
