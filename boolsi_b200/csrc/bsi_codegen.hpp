@@ -515,6 +515,8 @@ inline std::string generate_header(const Model &m, const std::vector<int> &filte
         for (int i = 0; i < n; ++i) o << " (P)[" << i << " * (S)] = X##" << i << ";";
         o << " }\n#define BSI_LOAD_MEM(X, P, S) {";
         for (int i = 0; i < n; ++i) o << " X##" << i << " = (P)[" << i << " * (S)];";
+        o << " }\n#define BSI_LOAD_STREAM(X, P, S) {";
+        for (int i = 0; i < n; ++i) o << " X##" << i << " = bsi_ld_stream((P) + " << i << " * (S));";
         o << " }\n#define BSI_DUMP(X, A) {";
         for (int i = 0; i < n; ++i) o << " (A)[" << i << "] = X##" << i << ";";
         o << " }\n";

@@ -314,6 +314,30 @@ __device__ __forceinline__ void bsi_dict_head_cg(const BsiDictSlot *s, u32 &f, u
     asm("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f), "=r"(idx), "=r"(base), "=r"(lam) : "l"(s));
 #endif
 }
+// Read-once data (the early-word queue: 1.1 GB per 2^26 states, every entry read by exactly one
+// thread): streaming loads (ld.global.cs, evict-first), so that the queue does not push the
+// resolution kernels' local-memory arrays out of the L2 on its way through.  (BSI_TUNE 128: plain loads.)
+__device__ __forceinline__ u32 bsi_ld_stream(const u32 *p) {
+#if defined(BSI_HOST_EMUL) || (BSI_TUNE & 128)
+    return *p;
+#else
+    return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ u64 bsi_ld_stream(const u64 *p) {
+#if defined(BSI_HOST_EMUL) || (BSI_TUNE & 128)
+    return *p;
+#else
+    return (u64)__ldcs((const unsigned long long *)p);
+#endif
+}
+// a found-queue record, read once (throughput-mode resolution): streaming loads as well
+__device__ __forceinline__ BsiFound bsi_found_stream(const BsiFound *p) {
+    union { BsiFound r; u64 w[sizeof(BsiFound) / 8]; } u;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(BsiFound) / 8); ++i) u.w[i] = bsi_ld_stream((const u64 *)p + i);
+    return u.r;
+}
 __device__ __forceinline__ u64 bsi_ldcg_u64(const u64 *p) {
 #ifdef BSI_HOST_EMUL
     return *((const volatile u64 *)p);
@@ -1267,7 +1291,7 @@ __device__ __forceinline__ void bsi_mu_word(BsiFound *found_q, u64 n_found, u64 
             for (int i = 0; i < BSI_KW; ++i) { cw_[l][i] = 0ull; cz_[l][i] = 0ull; x_[i] = 0ull; }
             keep->lam[l] = 0u;
             if (q < n_found) {
-                const BsiFound r = found_q[q];
+                const BsiFound r = KEEP ? bsi_found_stream(found_q + q) : found_q[q];
                 valid |= 1u << l;
                 const u32 adv = r.lam == 1u ? 0u : (r.lam - (r.c - r.c0) % r.lam) % r.lam;
                 aux_s[l * BSI_BLOCK + tid] = adv;
@@ -1733,7 +1757,7 @@ __device__ __noinline__ bool bsi_early_dict(const BsiDict &dict, const u32 *y, u
     u32 lam_[32], adv_[32], dbase_[32];
     {
         BSI_FOR_NODES(BSI_DECL_B)
-        BSI_LOAD_MEM(b, y, 32)
+        BSI_LOAD_STREAM(b, y, 32)
         BSI_UNPACK(cw_, b)
     }
 #pragma unroll 1
@@ -1793,15 +1817,15 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
         BSI_FOR_NODES(BSI_DECL_B)
         BSI_FOR_NODES(BSI_DECL_C)
         const BsiEarlyEntry ent = bsi_early_entry(eq, e);
-        const u32 valid = ent.mask[0];
-        const u32 info = ent.info[0];
+        const u32 valid = bsi_ld_stream(ent.mask);
+        const u32 info = bsi_ld_stream(ent.info);
         const u32 n_ev = info & 0xFFu, j_end = info >> 8;
-        const u64 W_ = ent.word[0];
+        const u64 W_ = bsi_ld_stream(ent.word);
         u32 evm[32], evl[32], eva[32];
         // (all event loads first, independent and in flight together)
 #pragma unroll 8
         for (u32 k = 0; k < 32; ++k)
-            if (k < n_ev) { evm[k] = ent.evm[k * 32u]; evl[k] = ent.evl[k * 32u]; }
+            if (k < n_ev) { evm[k] = bsi_ld_stream(ent.evm + k * 32u); evl[k] = bsi_ld_stream(ent.evl + k * 32u); }
         u32 lam_max = 0u, next_ = 0xFFFFFFFFu;
 #pragma unroll 1
         for (u32 k = 0; k < n_ev; ++k) {
@@ -1819,7 +1843,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
             if (via_dict) { BSI_COUNT(2) } else { BSI_COUNT(3) }
         }
         if (!via_dict) {
-            BSI_LOAD_MEM(b, ent.y, 32)
+            BSI_LOAD_STREAM(b, ent.y, 32)
             BSI_FOR_NODES(BSI_COPY_CB_)
             if (lam_max > 1u) {
                 // ---- keys (running minimum in c) and P(0) (latched into pb_) in one walk from y -----
@@ -1907,7 +1931,7 @@ __device__ __forceinline__ void bsi_early_word(const BsiEarlyQ &eq, u64 e, u64 T
         // ---- a <- x_0 from the problem-index word, b <- P(0) -------------------------------------
         BSI_INIT_DENSE(a, W_)
         BSI_PREFIX(BSI_LP_ORIGIN)
-        if (lam_max > 1u) { BSI_LOAD_MEM(b, pb_, 1) } else { BSI_LOAD_MEM(b, ent.y, 32) }
+        if (lam_max > 1u) { BSI_LOAD_MEM(b, pb_, 1) } else { BSI_LOAD_STREAM(b, ent.y, 32) }
         // ---- lock-step: mu = first j with x_j == P(j) -------------------------------------------
         u32 alive = valid;
 #define BSI_LOCK_CMP(A, B, J)                                                     \
