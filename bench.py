@@ -420,6 +420,15 @@ def run_gpu(a, name, cfg):
             else:
                 line['cpu_baseline'] = cpu_c_port(cfg, args, n, 8.0, cores)
             line['cpu_baseline_c'] = cpu_c_port(cfg, args, n, 8.0, cores)
+            if attract:
+                # BASELINE.json configs[0] / configs[1]: what a FRESH process pays for an 8-trajectory job --
+                # cold, with the compiled kernels on disk, and the reference's masters on the host
+                try:
+                    sys.path.insert(0, os.path.join(REPO, 'tools'))
+                    import cold_start
+                    line['small_jobs'] = cold_start.measure(['attract_example2', 'simulate_glider_t100'])
+                except Exception as e:      # noqa: BLE001  (an extra: never fails the bench line)
+                    line['small_jobs'] = {'unavailable': repr(e)[-300:]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -68,13 +68,12 @@ def child(case, impl, env):
             r['python_laps'] = [ln[4:] for ln in out.stdout.splitlines() if ln.startswith('LAP ')]
             laps = [ln[6:].split() for ln in out.stderr.splitlines() if ln.startswith('[bsi] ')]
             if laps:        # BSI_DEBUG_TIMING=1: the library's own stages, ms
-                r['stages_ms'] = [[' '.join(x[:-2]), float(x[-2])] for x in laps if len(x) >= 3]
+                r['stages_ms'] = [[' '.join(x[:-2]), float(x[-2])] for x in laps if len(x) >= 3 and float(x[-2]) >= 5.0]
             return r
     raise RuntimeError('child failed:\n' + out.stdout[-2000:] + out.stderr[-4000:])
 
 
-def main():
-    cases = (sys.argv[1] if len(sys.argv) > 1 else 'attract_example2,simulate_glider_t100').split(',')
+def measure(cases):
     line = {}
     for case in cases:
         with tempfile.TemporaryDirectory() as cache:
@@ -87,7 +86,12 @@ def main():
             line[case]['reference_cpu'] = {'unavailable': str(e)[-300:]}
     line['note'] = 'process_s: wall time of a fresh python process from its first line to the results (imports, ' \
                    'input decoding, CUDA context, kernel specialisation, run); job_s: the master call and its imports only'
-    print(json.dumps(line))
+    return line
+
+
+def main():
+    cases = (sys.argv[1] if len(sys.argv) > 1 else 'attract_example2,simulate_glider_t100').split(',')
+    print(json.dumps(measure(cases)))
 
 
 if __name__ == '__main__':
