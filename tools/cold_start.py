@@ -60,7 +60,7 @@ print('RESULT %%d %%.4f %%.4f' %% (n, t1 - t0, t1 - t_in))
 
 def child(case, impl, env):
     code = CHILD % {'repo': REPO, 'case': case, 'impl': impl}
-    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=90)
     for line in out.stdout.splitlines():
         if line.startswith('RESULT'):
             _, n, total, job = line.split()
