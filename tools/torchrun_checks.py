@@ -43,7 +43,6 @@ tts = [{(False,): False, (True,): True} for _ in range(n)]
 eng = AttractEngine(preds, tts, ([False] * n, {}, {}), (list(range(n)), [], []), device=local, rank=rank, world=world,
                     table_log2_slots=9)
 try:
-    from boolsi_b200.sharding import DEFAULT_CAPACITY  # noqa: F401
     eng.run(inf, inf)
     assert eng.plan_opts['table_log2_slots'] >= 15, eng.plan_opts
     assert eng.plan.table_count() == 1 << n and eng.totals['n_found'] == 1 << n, (eng.plan.table_count(), eng.totals)
