@@ -144,7 +144,8 @@ def test_emulated_extraction_of_final_checkpoint_states(n_nodes, k, seed, tune, 
     _check(exe, space, 5, 300, 90, 40, first_horizon=4)
 
 
-@pytest.mark.parametrize('n_nodes,k,seed,max_t', [(160, 2, 3, 300), (256, 2, 1, 400)])
+# (160 and 200 nodes run on the device: tests/test_gpu_large.py)
+@pytest.mark.parametrize('n_nodes,k,seed,max_t', [(256, 2, 1, 400)])
 def test_emulated_kernels_at_the_maximum_network_size(n_nodes, k, seed, max_t, tmp_path):
     """Three and four key words per state: beyond the golden fixtures (128 nodes)."""
     cfg = synth.random_attract_problem(n_nodes, k, seed, n_free=7)
