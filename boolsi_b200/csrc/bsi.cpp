@@ -1670,6 +1670,12 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
         uint64_t T = max_t;
         int check_closure = 0, n_chunks = 0;
         CUdeviceptr none = 0;
+        // the list's length after every chunk stays on the device (misc3[k], copied there in stream order):
+        // chunks run one after the other, so the hits of chunk k lie before those of chunk k + 1 in the
+        // list, and the first `cap` hits in index order are all within the prefix that ends with the
+        // first chunk whose running count reaches `cap` -- only that prefix is fetched and ordered
+        const uint64_t total_chunks = (total + chunk - 1) / chunk + 1;
+        if ((rc = ensure(p, p->misc3, 8 * total_chunks))) return rc;
         for (uint64_t b = idx_begin; b < idx_end;) {
             uint64_t e = std::min(idx_end, b + chunk);
             uint64_t n_in = e - b;
@@ -1678,6 +1684,7 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
                             &none, &none, &p->ctr.p};
             uint64_t n_words = (n_in + 31) >> 5;
             if ((rc = launch(p, p->f_target, (unsigned)((n_words + p->block - 1) / p->block), p->block, 0, args))) return rc;
+            CU_CHECK(cuMemcpyDtoDAsync(p->misc3.p + 8 * (uint64_t)st.rounds, p->ctr.p + offsetof(Counters, n_hits), 8, p->stream));
             ++st.rounds;
             b = e;
             // (a progress hook wants to hear from a long run: wait for the device every 16 chunks)
@@ -1690,8 +1697,17 @@ int bsi_target_run(bsi_plan *p, uint64_t idx_begin, uint64_t idx_end, uint64_t m
         Counters c;
         if ((rc = read_counters(p, &c))) return rc;
         if (c.n_hits <= hit_cap) {
-            if (c.n_hits && (rc = fetch_hits(c.n_hits))) return rc;
+            uint64_t fetch = c.n_hits;
+            if (cap < c.n_hits && st.rounds > 1) {
+                std::vector<uint64_t> after(st.rounds);
+                CU_CHECK(cuMemcpyDtoHAsync(after.data(), p->misc3.p, 8 * st.rounds, p->stream));
+                CU_CHECK(cuStreamSynchronize(p->stream));
+                for (uint64_t k = 0; k < st.rounds; ++k)
+                    if (after[k] >= cap) { fetch = std::min(fetch, after[k]); break; }
+            }
+            if (fetch && (rc = fetch_hits(fetch))) return rc;
             emit_sorted();
+            total_hits = c.n_hits;              // (the list was read in part only)
             done = true;
         } else {
             // (start over: the counters of the attempt are dropped)
